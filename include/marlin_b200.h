@@ -1,0 +1,171 @@
+/*
+ * marlin_b200.h — C ABI of libmarlin_b200.so, the B200 (sm_100a) drop-in for the dense
+ * block-matrix hot path of PasaLab/marlin (edu.nju.pasalab.marlin.matrix).
+ *
+ * The reference has no FFI of its own; its only native seam is Breeze -> netlib-java
+ * BLAS.dgemm (third-party, not in the tree).  The entry points below are what a JNI veneer
+ * for edu.nju.pasalab.marlin.matrix.{SubMatrix,BlockMatrix,DenseVecMatrix} and
+ * edu.nju.pasalab.marlin.utils.MTUtils would bind (see INTEGRATION.md for the Scala/JNI side).
+ * Every entry cites the reference code it replaces (paths relative to the reference's
+ * src/main/scala/edu/nju/pasalab/marlin/).
+ *
+ * Conventions
+ *   - plain C, no torch / C++ types; all functions return int32 status (0 = MB_OK, <0 = error);
+ *     mb_last_error() returns a thread-local message for the last failing call.
+ *   - one mb_ctx per process and GPU (one process per GPU, like one Spark executor per device).
+ *   - a block (mb_block) is the device-resident analogue of SubMatrix.denseBlock: Breeze
+ *     DenseMatrix semantics (data, offset, rows, cols, majorStride, isTranspose), column-major:
+ *        element(r,c) = data[offset + r + c*ld]            if !is_transpose
+ *                     = data[offset + c + r*ld]            if  is_transpose
+ *   - there is NO CPU fallback: without a CUDA device every compute entry returns MB_ERR_CUDA.
+ */
+#ifndef MARLIN_B200_H
+#define MARLIN_B200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)   /* the library is built with -fvisibility=hidden */
+#endif
+
+#define MB_OK                 0
+#define MB_ERR_INVALID_ARG   -1   /* -> IllegalArgumentException on the JVM side            */
+#define MB_ERR_DIM_MISMATCH  -2   /* -> IllegalArgumentException ("Dimension mismatch ...")  */
+#define MB_ERR_UNSUPPORTED   -3   /* -> IllegalArgumentException ("currently not supported") */
+#define MB_ERR_CUDA          -4   /* -> RuntimeException                                     */
+#define MB_ERR_OOM           -5
+#define MB_ERR_EMPTY         -6   /* -> RuntimeException (empty RDD: DistributedMatrixSuite "empty rows") */
+
+typedef enum { MB_F64 = 0, MB_BF16 = 1, MB_F32 = 2 } mb_dtype;
+
+typedef struct mb_ctx   mb_ctx;
+typedef struct mb_block mb_block;
+
+/* ---- lifetime (SparkContext lifetime in the reference) --------------------------------- */
+int32_t     mb_init(int32_t device, mb_ctx** out);
+int32_t     mb_shutdown(mb_ctx* ctx);
+const char* mb_last_error(void);
+const char* mb_version(void);
+/* Use an externally owned stream (e.g. torch's current stream) for every later call; 0 = own stream. */
+int32_t     mb_set_stream(mb_ctx* ctx, void* cuda_stream);
+int32_t     mb_synchronize(mb_ctx* ctx);
+/* Number of kernels this library has launched on ctx since init (bench.py's gpu_launches). */
+int64_t     mb_launch_count(mb_ctx* ctx);
+/* CUDA-event timing on the ctx stream, so callers can time kernels on the launching stream. */
+int32_t     mb_timer_start(mb_ctx* ctx);
+int32_t     mb_timer_stop(mb_ctx* ctx, float* ms_out);
+
+/* ---- blocks: `new SubMatrix(denseMatrix = ...)` (matrix/SubMatrix.scala:16-20) ---------- */
+int32_t mb_block_alloc(mb_ctx* ctx, int32_t rows, int32_t cols, mb_dtype dtype, mb_block** out);
+/* Non-owning view over device memory someone else allocated (torch tensor, NCCL buffer). */
+int32_t mb_block_wrap(mb_ctx* ctx, void* device_ptr, int64_t offset, int32_t rows, int32_t cols,
+                      int32_t ld, int32_t is_transpose, mb_dtype dtype, mb_block** out);
+/* Host fp64 (Breeze data/offset/majorStride/isTranspose) -> packed device block (ld = rows),
+ * optionally rounded to bf16 (round-to-nearest-even) for the bf16 path. */
+int32_t mb_block_upload(mb_ctx* ctx, const double* host, int64_t offset, int32_t rows, int32_t cols,
+                        int32_t ld, int32_t is_transpose, mb_dtype store_as, mb_block** out);
+/* toBreeze()/collect (matrix/BlockMatrix.scala:70-85): packed column-major fp64, leading dim ld. */
+int32_t mb_block_download(mb_ctx* ctx, const mb_block* blk, double* host, int32_t ld);
+int32_t mb_block_free(mb_ctx* ctx, mb_block* blk);
+int32_t mb_block_info(const mb_block* blk, int32_t* rows, int32_t* cols, int32_t* ld,
+                      int32_t* is_transpose, int32_t* dtype, void** device_ptr);
+/* Breeze `.t` (no copy) and `m(r0 until r1, c0 until c1)` (a view, majorStride = parent rows),
+ * as used by BlockMatrix.scala:198,213,299. */
+int32_t mb_block_view_t(mb_ctx* ctx, const mb_block* blk, mb_block** out);
+int32_t mb_block_slice(mb_ctx* ctx, const mb_block* blk, int32_t r0, int32_t r1, int32_t c0, int32_t c1,
+                       mb_block** out);
+
+/* ---- a1: SubMatrix.multiply (matrix/SubMatrix.scala:87-91, :107-111; inline twins
+ *      matrix/DenseVecMatrix.scala:122,129,1676) -> Breeze `*` -> netlib dgemm -------------- */
+/* C = A*B (accumulate=0) or C += A*B (accumulate=1; the k-way reduceByKey sum of
+ * BlockMatrix.scala:177 fused into the product).  fp64: DMMA tensor-core kernel (TMA staged).
+ * bf16 inputs: tcgen05 kernel with fp32 TMEM accumulation, C may be F32 or BF16. */
+int32_t mb_block_gemm(mb_ctx* ctx, const mb_block* A, const mb_block* B, mb_block* C, int32_t accumulate);
+/* Same GEMM on raw device pointers (column-major, BLAS trans flags 'N'/'T'). */
+int32_t mb_dgemm_device(mb_ctx* ctx, char transa, char transb, int32_t m, int32_t n, int32_t k,
+                        double alpha, const double* A, int32_t lda, const double* B, int32_t ldb,
+                        double beta, double* C, int32_t ldc);
+/* The third-party seam itself: com.github.fommil.netlib.BLAS.dgemm(transa, transb, m, n, k, alpha,
+ * a, aOffset, lda, b, bOffset, ldb, beta, c, cOffset, ldc) with HOST arrays (JVM double[]).
+ * Uploads, multiplies on the GPU, downloads C.  This is the end-to-end (e2e) entry bench.py times. */
+int32_t mb_dgemm_host(mb_ctx* ctx, char transa, char transb, int32_t m, int32_t n, int32_t k,
+                      double alpha, const double* a, int64_t a_offset, int32_t lda,
+                      const double* b, int64_t b_offset, int32_t ldb,
+                      double beta, double* c, int64_t c_offset, int32_t ldc);
+/* Force the generic (non-TMA, CUDA-core DFMA) kernel: test hook + path for odd ld / unaligned views. */
+int32_t mb_dgemm_device_generic(mb_ctx* ctx, char transa, char transb, int32_t m, int32_t n, int32_t k,
+                                double alpha, const double* A, int32_t lda, const double* B, int32_t ldb,
+                                double beta, double* C, int32_t ldc);
+
+/* ---- a2/a10: SubMatrix.add/subtract/scalar ops (matrix/SubMatrix.scala:41-85,123-131),
+ *      BlockMatrix.subtractBy/divideBy (matrix/BlockMatrix.scala:414-452) ------------------- */
+int32_t mb_block_add(mb_ctx* ctx, const mb_block* A, const mb_block* B, mb_block* out);      /* A + B */
+int32_t mb_block_sub(mb_ctx* ctx, const mb_block* A, const mb_block* B, mb_block* out);      /* A - B */
+int32_t mb_block_hadamard(mb_ctx* ctx, const mb_block* A, const mb_block* B, mb_block* out); /* A :* B (BlockMatrix.scala:494-500) */
+/* out = alpha*A + beta  (add(b): alpha=1; multiply(b): beta=0; subtractBy(b): alpha=-1, beta=b) */
+int32_t mb_block_axpb(mb_ctx* ctx, const mb_block* A, double alpha, double beta, mb_block* out);
+/* out = A / b  (true IEEE division, SubMatrix.divide) and out = b / A (divideBy) */
+int32_t mb_block_div(mb_ctx* ctx, const mb_block* A, double b, int32_t b_over_a, mb_block* out);
+/* ---- a9: BlockMatrix.transpose -> denseBlock.t.copy (matrix/BlockMatrix.scala:514-523) -- */
+int32_t mb_block_transpose(mb_ctx* ctx, const mb_block* A, mb_block* out);
+/* Materialise a (possibly strided / transposed) view into a packed block (Breeze `.copy`). */
+int32_t mb_block_copy(mb_ctx* ctx, const mb_block* A, mb_block* out);
+/* BlockMatrix.sum per block (matrix/BlockMatrix.scala:467-472) */
+int32_t mb_block_sum(mb_ctx* ctx, const mb_block* A, double* sum_out);
+
+/* ---- a11: MTUtils.randomDenVecMatrix / randomBlockMatrix input generation
+ *      (utils/MTUtils.scala:34-73, rdd/RandomRDD.scala:28-101, utils/RandomDataGenerator.scala:53-65,113-131).
+ * Fills `count` consecutive values of partition stream `partition_seed` (one XORShift stream per
+ * RDD partition), bit-exact with UniformGenerator(lo,hi).nextValue(), starting at value index
+ * `first` of that stream, written into blk in the order the reference fills it
+ * (row_major=1: DenseVecMatrix rows, Array.fill(cols); row_major=0: BDM.create column-major). */
+int32_t mb_fill_uniform(mb_ctx* ctx, mb_block* blk, int64_t partition_seed, int64_t first,
+                        double lo, double hi, int32_t row_major);
+/* Host-side pieces of the same generator (pure integer logic, exported for the host mirror):
+ * MTUtils.hashSeed (MurmurHash3.bytesHash over a 64-byte buffer) and the per-partition seeds
+ * = successive java.util.Random(seed).nextLong() (rdd/RandomRDD.scala:28-45). */
+int64_t mb_hash_seed(int64_t seed);
+int32_t mb_partition_seeds(int64_t seed, int32_t num_partitions, int64_t* seeds_out);
+
+/* ---- a7/a8: strategy + partitioning (pure integer logic) --------------------------------- */
+/* MTUtils.splitMethod(m,k,n,cores) (utils/MTUtils.scala:150-175, dimToSplit :204-213) */
+int32_t mb_choose_split(int64_t m, int64_t k, int64_t n, int32_t cores, int32_t out_mkn[3]);
+/* DenseVecMatrix.multiply(other,cores,broadcastThreshold) chooser (matrix/DenseVecMatrix.scala:196-231,
+ * matrix/BlockMatrix.scala:87-122).  other_is_block selects the `case that: BlockMatrix` arm.
+ * Returns strategy in *strategy: 0 = broadcast B (this.multiply(that.toBreeze())),
+ * 1 = broadcast A (the reference's quirk arm), 2 = shuffle with out_mkn. */
+int32_t mb_choose_strategy(int64_t a_rows, int64_t a_cols, int64_t b_cols, int32_t cores,
+                           int32_t broadcast_threshold_mb, int32_t other_is_block,
+                           int32_t* strategy, int32_t out_mkn[3]);
+/* MatrixMultPartitioner (rdd/MatrixMultPartitioner.scala:12-22) with the seq formula of
+ * matrix/BlockMatrix.scala:163,168: seq = i*n*k + j*k + kk. */
+int32_t mb_mult_partition(int32_t i, int32_t j, int32_t kk, int32_t m, int32_t k, int32_t n);
+/* MatrixElemOpPartitioner (rdd/MatrixElemOpPartitioner.scala:16) */
+int32_t mb_elem_partition(int32_t row, int32_t col, int32_t blks_by_col);
+/* ceil-based block sizing (matrix/BlockMatrix.scala:73-74, matrix/DenseVecMatrix.scala:1091-1094):
+ * block length = ceil(total/parts); actual number of blocks = ceil(total/block_len). */
+int32_t mb_block_len(int64_t total, int32_t parts, int32_t* block_len, int32_t* actual_parts);
+
+/* ---- a3/a4: BlockMatrix.multiply(other: BlockMatrix) on ONE device
+ *      (matrix/BlockMatrix.scala:149-186): all m*k*n block products in seq order, the k partials of
+ *      each C tile accumulated in place.  A_tiles[i*k+kk], B_tiles[kk*n+j], C_tiles[i*n+j]
+ *      (MatrixElemOpPartitioner order).  Multi-GPU sharding of the seq list is done by the host
+ *      (marlin_b200.matrix.BlockMatrix) with one process per GPU. */
+int32_t mb_matmul_blocked(mb_ctx* ctx, mb_block* const* A_tiles, mb_block* const* B_tiles,
+                          int32_t m, int32_t k, int32_t n, mb_block* const* C_tiles);
+
+/* ---- rows <-> blocks on device (matrix/DenseVecMatrix.scala:1084-1223, 1259-1328;
+ *      matrix/BlockMatrix.scala:575-594): a DenseVecMatrix shard is a row-major (rows x cols)
+ *      buffer, i.e. a transposed block; these are strided copies (mb_block_copy on views). */
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* MARLIN_B200_H */

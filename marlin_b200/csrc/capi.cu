@@ -1,0 +1,554 @@
+// C ABI of libmarlin_b200.so (see include/marlin_b200.h).  Context, block handles and dispatch.
+// There is no CPU fallback anywhere in this file: without a CUDA device mb_init fails with
+// MB_ERR_CUDA and no compute entry can be reached.
+#include "../../include/marlin_b200.h"
+#include "elementwise.h"
+#include "gemm_f64.h"
+#include "gemm_bf16.h"
+
+#include <cuda_runtime.h>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <atomic>
+
+struct mb_ctx {
+    int device = 0;
+    int num_sms = 148;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    std::atomic<long long> launches{0};
+    double* scratch = nullptr;          // sum partials + result
+    double* host_scalar = nullptr;      // pinned
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+
+struct mb_block {
+    void* data = nullptr;      // device base pointer (element 0 of the underlying array)
+    long long offset = 0;      // in elements
+    int rows = 0, cols = 0;    // logical dims
+    int ld = 0;                // majorStride
+    int is_transpose = 0;
+    int dtype = MB_F64;
+    int owns = 0;
+    int device = 0;
+};
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int32_t fail(int32_t code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+int32_t cuda_fail(cudaError_t e, const char* what) {
+    return fail(e == cudaErrorMemoryAllocation ? MB_ERR_OOM : MB_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+}
+#define MB_CUDA(call)                                       \
+    do {                                                    \
+        cudaError_t _e = (call);                            \
+        if (_e != cudaSuccess) return cuda_fail(_e, #call); \
+    } while (0)
+
+inline size_t elem_size(int dtype) { return dtype == MB_F64 ? 8 : (dtype == MB_F32 ? 4 : 2); }
+inline char* elem_ptr(const mb_block* b) { return static_cast<char*>(b->data) + b->offset * (long long)elem_size(b->dtype); }
+inline double* f64_ptr(const mb_block* b) { return reinterpret_cast<double*>(elem_ptr(b)); }
+// strides of the logical (rows x cols) view
+inline long long rs(const mb_block* b) { return b->is_transpose ? b->ld : 1; }
+inline long long cs(const mb_block* b) { return b->is_transpose ? 1 : b->ld; }
+
+int32_t check_ctx(mb_ctx* ctx) {
+    if (!ctx) return fail(MB_ERR_INVALID_ARG, "null context");
+    cudaError_t e = cudaSetDevice(ctx->device);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
+    return MB_OK;
+}
+#define MB_CTX(ctx)                        \
+    do {                                   \
+        int32_t _r = check_ctx(ctx);       \
+        if (_r != MB_OK) return _r;        \
+    } while (0)
+
+int32_t new_block(mb_block** out) {
+    *out = new (std::nothrow) mb_block();
+    if (!*out) return fail(MB_ERR_OOM, "host allocation failed");
+    return MB_OK;
+}
+
+int32_t same_shape(const mb_block* a, const mb_block* b, const char* what) {
+    if (a->rows != b->rows || a->cols != b->cols)
+        return fail(MB_ERR_DIM_MISMATCH, "matrix dimension mismatch in %s: %dx%d vs %dx%d", what, a->rows, a->cols,
+                    b->rows, b->cols);
+    return MB_OK;
+}
+
+int32_t binary_op(mb_ctx* ctx, int op, const mb_block* A, const mb_block* B, mb_block* out, const char* name) {
+    MB_CTX(ctx);
+    if (!A || !B || !out) return fail(MB_ERR_INVALID_ARG, "%s: null block", name);
+    int32_t r = same_shape(A, B, name);
+    if (r) return r;
+    r = same_shape(A, out, name);
+    if (r) return r;
+    if (A->dtype != MB_F64 || B->dtype != MB_F64 || out->dtype != MB_F64)
+        return fail(MB_ERR_UNSUPPORTED, "%s: fp64 blocks only (convert bf16 blocks with mb_block_copy)", name);
+    // iterate in the output's storage order so the store side is contiguous
+    int rows = A->rows, cols = A->cols;
+    long long ars = rs(A), acs = cs(A), brs = rs(B), bcs = cs(B), ors = rs(out), ocs = cs(out);
+    if (out->is_transpose) {
+        std::swap(rows, cols);
+        std::swap(ars, acs); std::swap(brs, bcs); std::swap(ors, ocs);
+    }
+    MB_CUDA(mb::ew_binary(op, rows, cols, f64_ptr(A), ars, acs, f64_ptr(B), brs, bcs, f64_ptr(out), ors, ocs, ctx->stream));
+    ctx->launches++;
+    return MB_OK;
+}
+
+int32_t unary_op(mb_ctx* ctx, int op, const mb_block* A, mb_block* out, double alpha, double beta, const char* name) {
+    MB_CTX(ctx);
+    if (!A || !out) return fail(MB_ERR_INVALID_ARG, "%s: null block", name);
+    int32_t r = same_shape(A, out, name);
+    if (r) return r;
+    if (A->dtype != MB_F64 || out->dtype != MB_F64)
+        return fail(MB_ERR_UNSUPPORTED, "%s: fp64 blocks only", name);
+    int rows = A->rows, cols = A->cols;
+    long long ars = rs(A), acs = cs(A), ors = rs(out), ocs = cs(out);
+    if (out->is_transpose) {
+        std::swap(rows, cols);
+        std::swap(ars, acs); std::swap(ors, ocs);
+    }
+    MB_CUDA(mb::ew_unary(op, rows, cols, f64_ptr(A), ars, acs, f64_ptr(out), ors, ocs, alpha, beta, ctx->stream));
+    ctx->launches++;
+    return MB_OK;
+}
+
+// out (col-major packed or strided, same logical shape as `A` view) = A, with dtype conversion.
+int32_t copy_convert(mb_ctx* ctx, const mb_block* A, mb_block* out) {
+    int rows = A->rows, cols = A->cols;
+    long long ars = rs(A), acs = cs(A), ors = rs(out), ocs = cs(out);
+    if (out->is_transpose) {
+        std::swap(rows, cols);
+        std::swap(ars, acs); std::swap(ors, ocs);
+    }
+    if (A->dtype == MB_F64 && out->dtype == MB_F64) {
+        if (ars == 1 && ors == 1) {
+            MB_CUDA(mb::ew_unary(mb::EW_COPY, rows, cols, f64_ptr(A), ars, acs, f64_ptr(out), ors, ocs, 1.0, 0.0, ctx->stream));
+        } else if (acs == 1 && ors == 1) {
+            // source is the transpose of a column-major (cols x rows, ld = ars) array
+            MB_CUDA(mb::transpose_f64(f64_ptr(A), ars, f64_ptr(out), ocs, cols, rows, ctx->stream));
+        } else {
+            MB_CUDA(mb::ew_unary(mb::EW_COPY, rows, cols, f64_ptr(A), ars, acs, f64_ptr(out), ors, ocs, 1.0, 0.0, ctx->stream));
+        }
+    } else if (A->dtype == out->dtype && acs == 1 && ors == 1 && A->dtype == MB_BF16) {
+        MB_CUDA(mb::transpose_b16(elem_ptr(A), ars, elem_ptr(out), ocs, cols, rows, ctx->stream));
+    } else if (A->dtype == out->dtype && acs == 1 && ors == 1 && A->dtype == MB_F32) {
+        MB_CUDA(mb::transpose_b32(elem_ptr(A), ars, elem_ptr(out), ocs, cols, rows, ctx->stream));
+    } else {
+        MB_CUDA(mb::convert_strided(A->dtype, out->dtype, rows, cols, elem_ptr(A), ars, acs, elem_ptr(out), ors, ocs, ctx->stream));
+    }
+    ctx->launches++;
+    return MB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* mb_last_error(void) { return g_err; }
+const char* mb_version(void) { return "marlin_b200 0.1 (sm_100a)"; }
+
+int32_t mb_init(int32_t device, mb_ctx** out) {
+    if (!out) return fail(MB_ERR_INVALID_ARG, "mb_init: null out");
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(MB_ERR_CUDA, "mb_init: no CUDA device (%s); marlin_b200 has no CPU fallback",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    if (device < 0 || device >= count) return fail(MB_ERR_INVALID_ARG, "mb_init: device %d out of range [0,%d)", device, count);
+    MB_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    MB_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(MB_ERR_UNSUPPORTED, "mb_init: device %d is sm_%d%d; this library is built for sm_100a only", device,
+                    prop.major, prop.minor);
+    mb_ctx* ctx = new (std::nothrow) mb_ctx();
+    if (!ctx) return fail(MB_ERR_OOM, "host allocation failed");
+    ctx->device = device;
+    ctx->num_sms = prop.multiProcessorCount;
+    MB_CUDA(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
+    ctx->stream = ctx->own_stream;
+    MB_CUDA(cudaMalloc(&ctx->scratch, sizeof(double) * mb::sum_scratch_doubles()));
+    MB_CUDA(cudaMallocHost(&ctx->host_scalar, sizeof(double)));
+    MB_CUDA(cudaEventCreate(&ctx->ev0));
+    MB_CUDA(cudaEventCreate(&ctx->ev1));
+    *out = ctx;
+    return MB_OK;
+}
+
+int32_t mb_shutdown(mb_ctx* ctx) {
+    if (!ctx) return MB_OK;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->scratch) cudaFree(ctx->scratch);
+    if (ctx->host_scalar) cudaFreeHost(ctx->host_scalar);
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+    return MB_OK;
+}
+
+int32_t mb_set_stream(mb_ctx* ctx, void* cuda_stream) {
+    if (!ctx) return fail(MB_ERR_INVALID_ARG, "null context");
+    ctx->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->own_stream;
+    return MB_OK;
+}
+
+int32_t mb_synchronize(mb_ctx* ctx) {
+    MB_CTX(ctx);
+    MB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return MB_OK;
+}
+
+int64_t mb_launch_count(mb_ctx* ctx) { return ctx ? (int64_t)ctx->launches.load() : 0; }
+
+int32_t mb_timer_start(mb_ctx* ctx) {
+    MB_CTX(ctx);
+    MB_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+    return MB_OK;
+}
+int32_t mb_timer_stop(mb_ctx* ctx, float* ms_out) {
+    MB_CTX(ctx);
+    if (!ms_out) return fail(MB_ERR_INVALID_ARG, "null ms_out");
+    MB_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+    MB_CUDA(cudaEventSynchronize(ctx->ev1));
+    MB_CUDA(cudaEventElapsedTime(ms_out, ctx->ev0, ctx->ev1));
+    return MB_OK;
+}
+
+// ---------------------------------------------------------------------------------- blocks
+int32_t mb_block_alloc(mb_ctx* ctx, int32_t rows, int32_t cols, mb_dtype dtype, mb_block** out) {
+    MB_CTX(ctx);
+    if (!out || rows < 0 || cols < 0 || dtype < 0 || dtype > 2) return fail(MB_ERR_INVALID_ARG, "mb_block_alloc: bad argument");
+    int32_t r = new_block(out);
+    if (r) return r;
+    mb_block* b = *out;
+    b->rows = rows; b->cols = cols; b->ld = rows > 0 ? rows : 1; b->dtype = dtype; b->owns = 1; b->device = ctx->device;
+    const size_t bytes = (size_t)rows * (size_t)cols * elem_size(dtype);
+    if (bytes) {
+        cudaError_t e = cudaMalloc(&b->data, bytes);
+        if (e != cudaSuccess) { delete b; *out = nullptr; return cuda_fail(e, "cudaMalloc(block)"); }
+    }
+    return MB_OK;
+}
+
+int32_t mb_block_wrap(mb_ctx* ctx, void* device_ptr, int64_t offset, int32_t rows, int32_t cols, int32_t ld,
+                      int32_t is_transpose, mb_dtype dtype, mb_block** out) {
+    if (!ctx) return fail(MB_ERR_INVALID_ARG, "null context");
+    if (!out || rows < 0 || cols < 0 || offset < 0 || dtype < 0 || dtype > 2)
+        return fail(MB_ERR_INVALID_ARG, "mb_block_wrap: bad argument");
+    const int minor = is_transpose ? cols : rows;
+    if (ld < (minor > 0 ? minor : 1)) return fail(MB_ERR_INVALID_ARG, "mb_block_wrap: ld %d < %d", ld, minor);
+    int32_t r = new_block(out);
+    if (r) return r;
+    mb_block* b = *out;
+    b->data = device_ptr; b->offset = offset; b->rows = rows; b->cols = cols; b->ld = ld;
+    b->is_transpose = is_transpose ? 1 : 0; b->dtype = dtype; b->owns = 0; b->device = ctx->device;
+    return MB_OK;
+}
+
+int32_t mb_block_free(mb_ctx* ctx, mb_block* blk) {
+    if (!blk) return MB_OK;
+    if (blk->owns && blk->data) {
+        if (ctx) cudaSetDevice(ctx->device);
+        cudaFree(blk->data);
+    }
+    delete blk;
+    return MB_OK;
+}
+
+int32_t mb_block_info(const mb_block* blk, int32_t* rows, int32_t* cols, int32_t* ld, int32_t* is_transpose,
+                      int32_t* dtype, void** device_ptr) {
+    if (!blk) return fail(MB_ERR_INVALID_ARG, "null block");
+    if (rows) *rows = blk->rows;
+    if (cols) *cols = blk->cols;
+    if (ld) *ld = blk->ld;
+    if (is_transpose) *is_transpose = blk->is_transpose;
+    if (dtype) *dtype = blk->dtype;
+    if (device_ptr) *device_ptr = elem_ptr(blk);
+    return MB_OK;
+}
+
+int32_t mb_block_view_t(mb_ctx* ctx, const mb_block* blk, mb_block** out) {
+    if (!ctx || !blk || !out) return fail(MB_ERR_INVALID_ARG, "mb_block_view_t: null argument");
+    int32_t r = new_block(out);
+    if (r) return r;
+    **out = *blk;
+    (*out)->owns = 0;
+    std::swap((*out)->rows, (*out)->cols);
+    (*out)->is_transpose = !blk->is_transpose;
+    return MB_OK;
+}
+
+int32_t mb_block_slice(mb_ctx* ctx, const mb_block* blk, int32_t r0, int32_t r1, int32_t c0, int32_t c1, mb_block** out) {
+    if (!ctx || !blk || !out) return fail(MB_ERR_INVALID_ARG, "mb_block_slice: null argument");
+    if (r0 < 0 || r1 < r0 || r1 > blk->rows || c0 < 0 || c1 < c0 || c1 > blk->cols)
+        return fail(MB_ERR_INVALID_ARG, "mb_block_slice: range [%d,%d)x[%d,%d) outside %dx%d", r0, r1, c0, c1, blk->rows, blk->cols);
+    int32_t r = new_block(out);
+    if (r) return r;
+    **out = *blk;
+    (*out)->owns = 0;
+    (*out)->rows = r1 - r0;
+    (*out)->cols = c1 - c0;
+    (*out)->offset = blk->offset + r0 * rs(blk) + c0 * cs(blk);
+    return MB_OK;
+}
+
+int32_t mb_block_upload(mb_ctx* ctx, const double* host, int64_t offset, int32_t rows, int32_t cols, int32_t ld,
+                        int32_t is_transpose, mb_dtype store_as, mb_block** out) {
+    MB_CTX(ctx);
+    if (!host || !out || rows < 0 || cols < 0 || offset < 0) return fail(MB_ERR_INVALID_ARG, "mb_block_upload: bad argument");
+    const int minor = is_transpose ? cols : rows, major = is_transpose ? rows : cols;
+    if (ld < (minor > 0 ? minor : 1)) return fail(MB_ERR_INVALID_ARG, "mb_block_upload: ld %d < %d", ld, minor);
+    int32_t r = mb_block_alloc(ctx, rows, cols, store_as, out);
+    if (r) return r;
+    if (rows == 0 || cols == 0) return MB_OK;
+    // stage the raw (minor x major) host array, then one device kernel packs / transposes / rounds it
+    mb_block* dst = *out;
+    const bool direct = (store_as == MB_F64) && !is_transpose;
+    if (direct) {
+        cudaError_t e = cudaMemcpy2DAsync(dst->data, (size_t)rows * 8, host + offset, (size_t)ld * 8, (size_t)rows * 8,
+                                          (size_t)cols, cudaMemcpyHostToDevice, ctx->stream);
+        if (e != cudaSuccess) { mb_block_free(ctx, dst); *out = nullptr; return cuda_fail(e, "cudaMemcpy2DAsync(H2D)"); }
+        MB_CUDA(cudaStreamSynchronize(ctx->stream));
+        return MB_OK;
+    }
+    double* stage = nullptr;
+    MB_CUDA(cudaMalloc(&stage, (size_t)minor * major * 8));
+    cudaError_t e = cudaMemcpy2DAsync(stage, (size_t)minor * 8, host + offset, (size_t)ld * 8, (size_t)minor * 8,
+                                      (size_t)major, cudaMemcpyHostToDevice, ctx->stream);
+    if (e != cudaSuccess) { cudaFree(stage); mb_block_free(ctx, dst); *out = nullptr; return cuda_fail(e, "cudaMemcpy2DAsync(H2D)"); }
+    mb_block src;
+    src.data = stage; src.rows = rows; src.cols = cols; src.ld = minor; src.is_transpose = is_transpose ? 1 : 0; src.dtype = MB_F64;
+    r = copy_convert(ctx, &src, dst);
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(stage);
+    if (r) { mb_block_free(ctx, dst); *out = nullptr; }
+    return r;
+}
+
+int32_t mb_block_download(mb_ctx* ctx, const mb_block* blk, double* host, int32_t ld) {
+    MB_CTX(ctx);
+    if (!blk || !host) return fail(MB_ERR_INVALID_ARG, "mb_block_download: null argument");
+    if (ld < blk->rows) return fail(MB_ERR_INVALID_ARG, "mb_block_download: ld %d < rows %d", ld, blk->rows);
+    if (blk->rows == 0 || blk->cols == 0) return MB_OK;
+    const double* src = nullptr;
+    size_t src_pitch = 0;
+    double* stage = nullptr;
+    if (blk->dtype == MB_F64 && !blk->is_transpose) {
+        src = f64_ptr(blk);
+        src_pitch = (size_t)blk->ld * 8;
+    } else {
+        MB_CUDA(cudaMalloc(&stage, (size_t)blk->rows * blk->cols * 8));
+        mb_block tmp;
+        tmp.data = stage; tmp.rows = blk->rows; tmp.cols = blk->cols; tmp.ld = blk->rows; tmp.dtype = MB_F64;
+        int32_t r = copy_convert(ctx, blk, &tmp);
+        if (r) { cudaFree(stage); return r; }
+        src = stage;
+        src_pitch = (size_t)blk->rows * 8;
+    }
+    cudaError_t e = cudaMemcpy2DAsync(host, (size_t)ld * 8, src, src_pitch, (size_t)blk->rows * 8, (size_t)blk->cols,
+                                      cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (stage) cudaFree(stage);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemcpy2DAsync(D2H)");
+    return MB_OK;
+}
+
+// ------------------------------------------------------------------------------------ GEMM
+static int32_t dgemm_device_impl(mb_ctx* ctx, char transa, char transb, int32_t m, int32_t n, int32_t k, double alpha,
+                                 const double* A, int32_t lda, const double* B, int32_t ldb, double beta, double* C,
+                                 int32_t ldc, bool force_generic) {
+    MB_CTX(ctx);
+    const bool ta = (transa == 'T' || transa == 't' || transa == 'C' || transa == 'c');
+    const bool tb = (transb == 'T' || transb == 't' || transb == 'C' || transb == 'c');
+    if (!ta && !(transa == 'N' || transa == 'n')) return fail(MB_ERR_INVALID_ARG, "dgemm: transa '%c'", transa);
+    if (!tb && !(transb == 'N' || transb == 'n')) return fail(MB_ERR_INVALID_ARG, "dgemm: transb '%c'", transb);
+    if (m < 0 || n < 0 || k < 0) return fail(MB_ERR_INVALID_ARG, "dgemm: negative dimension");
+    const int nrowa = ta ? k : m, nrowb = tb ? n : k;
+    if (lda < (nrowa > 1 ? nrowa : 1) || ldb < (nrowb > 1 ? nrowb : 1) || ldc < (m > 1 ? m : 1))
+        return fail(MB_ERR_INVALID_ARG, "dgemm: leading dimension too small (lda=%d ldb=%d ldc=%d)", lda, ldb, ldc);
+    if (m == 0 || n == 0) return MB_OK;
+    if (!C || (k > 0 && alpha != 0.0 && (!A || !B))) return fail(MB_ERR_INVALID_ARG, "dgemm: null pointer");
+    int launches = 0;
+    MB_CUDA(mb::gemm_f64(ta, tb, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, ctx->num_sms, ctx->stream, force_generic, &launches));
+    ctx->launches += launches;
+    return MB_OK;
+}
+
+int32_t mb_dgemm_device(mb_ctx* ctx, char transa, char transb, int32_t m, int32_t n, int32_t k, double alpha,
+                        const double* A, int32_t lda, const double* B, int32_t ldb, double beta, double* C, int32_t ldc) {
+    return dgemm_device_impl(ctx, transa, transb, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, false);
+}
+int32_t mb_dgemm_device_generic(mb_ctx* ctx, char transa, char transb, int32_t m, int32_t n, int32_t k, double alpha,
+                                const double* A, int32_t lda, const double* B, int32_t ldb, double beta, double* C,
+                                int32_t ldc) {
+    return dgemm_device_impl(ctx, transa, transb, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, true);
+}
+
+int32_t mb_dgemm_host(mb_ctx* ctx, char transa, char transb, int32_t m, int32_t n, int32_t k, double alpha,
+                      const double* a, int64_t a_offset, int32_t lda, const double* b, int64_t b_offset, int32_t ldb,
+                      double beta, double* c, int64_t c_offset, int32_t ldc) {
+    MB_CTX(ctx);
+    const bool ta = (transa == 'T' || transa == 't'), tb = (transb == 'T' || transb == 't');
+    if (m < 0 || n < 0 || k < 0) return fail(MB_ERR_INVALID_ARG, "dgemm: negative dimension");
+    if (m == 0 || n == 0) return MB_OK;
+    if (!a || !b || !c) return fail(MB_ERR_INVALID_ARG, "dgemm: null host array");
+    const int ra = ta ? k : m, ca = ta ? m : k, rb = tb ? n : k, cb = tb ? k : n;
+    if (lda < (ra > 1 ? ra : 1) || ldb < (rb > 1 ? rb : 1) || ldc < (m > 1 ? m : 1))
+        return fail(MB_ERR_INVALID_ARG, "dgemm: leading dimension too small");
+    // device staging is packed with an even leading dimension so the TMA path is always eligible
+    auto even = [](int x) { return (x + 1) & ~1; };
+    const int dlda = even(ra > 0 ? ra : 1), dldb = even(rb > 0 ? rb : 1), dldc = even(m);
+    double *dA = nullptr, *dB = nullptr, *dC = nullptr;
+    cudaError_t e = cudaSuccess;
+    auto cleanup = [&]() { if (dA) cudaFree(dA); if (dB) cudaFree(dB); if (dC) cudaFree(dC); };
+    if (k > 0) {
+        if ((e = cudaMalloc(&dA, (size_t)dlda * ca * 8)) != cudaSuccess) { cleanup(); return cuda_fail(e, "cudaMalloc(A)"); }
+        if ((e = cudaMalloc(&dB, (size_t)dldb * cb * 8)) != cudaSuccess) { cleanup(); return cuda_fail(e, "cudaMalloc(B)"); }
+    }
+    if ((e = cudaMalloc(&dC, (size_t)dldc * n * 8)) != cudaSuccess) { cleanup(); return cuda_fail(e, "cudaMalloc(C)"); }
+    if (k > 0) {
+        e = cudaMemcpy2DAsync(dA, (size_t)dlda * 8, a + a_offset, (size_t)lda * 8, (size_t)ra * 8, ca, cudaMemcpyHostToDevice, ctx->stream);
+        if (e == cudaSuccess)
+            e = cudaMemcpy2DAsync(dB, (size_t)dldb * 8, b + b_offset, (size_t)ldb * 8, (size_t)rb * 8, cb, cudaMemcpyHostToDevice, ctx->stream);
+    }
+    if (e == cudaSuccess && beta != 0.0)
+        e = cudaMemcpy2DAsync(dC, (size_t)dldc * 8, c + c_offset, (size_t)ldc * 8, (size_t)m * 8, n, cudaMemcpyHostToDevice, ctx->stream);
+    if (e != cudaSuccess) { cleanup(); return cuda_fail(e, "H2D copy"); }
+    int32_t r = dgemm_device_impl(ctx, transa, transb, m, n, k, alpha, dA, dlda, dB, dldb, beta, dC, dldc, false);
+    if (r == MB_OK) {
+        e = cudaMemcpy2DAsync(c + c_offset, (size_t)ldc * 8, dC, (size_t)dldc * 8, (size_t)m * 8, n, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) r = cuda_fail(e, "D2H copy");
+    }
+    cleanup();
+    return r;
+}
+
+int32_t mb_block_gemm(mb_ctx* ctx, const mb_block* A, const mb_block* B, mb_block* C, int32_t accumulate) {
+    MB_CTX(ctx);
+    if (!A || !B || !C) return fail(MB_ERR_INVALID_ARG, "mb_block_gemm: null block");
+    if (A->cols != B->rows)
+        return fail(MB_ERR_DIM_MISMATCH, "Dimension mismatch during matrix-matrix multiplication: %d vs %d", A->cols, B->rows);
+    if (C->rows != A->rows || C->cols != B->cols)
+        return fail(MB_ERR_DIM_MISMATCH, "mb_block_gemm: result block is %dx%d, expected %dx%d", C->rows, C->cols, A->rows, B->cols);
+    const int M = A->rows, N = B->cols, K = A->cols;
+    if (A->dtype == MB_F64 && B->dtype == MB_F64 && C->dtype == MB_F64) {
+        if (!C->is_transpose) {
+            return dgemm_device_impl(ctx, A->is_transpose ? 'T' : 'N', B->is_transpose ? 'T' : 'N', M, N, K, 1.0, f64_ptr(A),
+                                     A->ld, f64_ptr(B), B->ld, accumulate ? 1.0 : 0.0, f64_ptr(C), C->ld, false);
+        }
+        // row-major result (DenseVecMatrix rows, matrix/DenseVecMatrix.scala:1660-1680): C^T = B^T * A^T,
+        // where X^T of a transposed view is the plain column-major array underneath.
+        return dgemm_device_impl(ctx, B->is_transpose ? 'N' : 'T', A->is_transpose ? 'N' : 'T', N, M, K, 1.0, f64_ptr(B),
+                                 B->ld, f64_ptr(A), A->ld, accumulate ? 1.0 : 0.0, f64_ptr(C), C->ld, false);
+    }
+    if (A->dtype == MB_BF16 && B->dtype == MB_BF16 && (C->dtype == MB_F32 || C->dtype == MB_BF16)) {
+        int launches = 0;
+        cudaError_t e;
+        if (!C->is_transpose) {
+            e = mb::gemm_bf16(A->is_transpose, B->is_transpose, M, N, K, elem_ptr(A), A->ld, elem_ptr(B), B->ld,
+                              elem_ptr(C), C->ld, C->dtype == MB_F32, accumulate != 0, ctx->num_sms, ctx->stream, &launches);
+        } else {
+            e = mb::gemm_bf16(!B->is_transpose, !A->is_transpose, N, M, K, elem_ptr(B), B->ld, elem_ptr(A), A->ld,
+                              elem_ptr(C), C->ld, C->dtype == MB_F32, accumulate != 0, ctx->num_sms, ctx->stream, &launches);
+        }
+        if (e == cudaErrorNotSupported)
+            return fail(MB_ERR_UNSUPPORTED, "mb_block_gemm(bf16): operands must be 16-byte aligned with ld %% 8 == 0");
+        if (e != cudaSuccess) return cuda_fail(e, "gemm_bf16");
+        ctx->launches += launches;
+        return MB_OK;
+    }
+    return fail(MB_ERR_UNSUPPORTED, "mb_block_gemm: unsupported dtype combination (%d,%d)->%d", A->dtype, B->dtype, C->dtype);
+}
+
+int32_t mb_matmul_blocked(mb_ctx* ctx, mb_block* const* A_tiles, mb_block* const* B_tiles, int32_t m, int32_t k,
+                          int32_t n, mb_block* const* C_tiles) {
+    MB_CTX(ctx);
+    if (!A_tiles || !B_tiles || !C_tiles || m <= 0 || k <= 0 || n <= 0)
+        return fail(MB_ERR_INVALID_ARG, "mb_matmul_blocked: bad argument");
+    // seq order of matrix/BlockMatrix.scala:163,168: p = i*n*k + j*k + kk; the kk partials of C(i,j)
+    // (reduceByKey at :177) are accumulated in place, kk ascending.
+    for (int i = 0; i < m; ++i)
+        for (int j = 0; j < n; ++j)
+            for (int kk = 0; kk < k; ++kk) {
+                int32_t r = mb_block_gemm(ctx, A_tiles[i * k + kk], B_tiles[kk * n + j], C_tiles[i * n + j], kk > 0);
+                if (r) return r;
+            }
+    return MB_OK;
+}
+
+// ----------------------------------------------------------------------------- elementwise
+int32_t mb_block_add(mb_ctx* ctx, const mb_block* A, const mb_block* B, mb_block* out) { return binary_op(ctx, mb::EW_ADD, A, B, out, "add"); }
+int32_t mb_block_sub(mb_ctx* ctx, const mb_block* A, const mb_block* B, mb_block* out) { return binary_op(ctx, mb::EW_SUB, A, B, out, "subtract"); }
+int32_t mb_block_hadamard(mb_ctx* ctx, const mb_block* A, const mb_block* B, mb_block* out) { return binary_op(ctx, mb::EW_MUL, A, B, out, "dotProduct"); }
+int32_t mb_block_axpb(mb_ctx* ctx, const mb_block* A, double alpha, double beta, mb_block* out) {
+    return unary_op(ctx, mb::EW_AXPB, A, out, alpha, beta, "axpb");
+}
+int32_t mb_block_div(mb_ctx* ctx, const mb_block* A, double b, int32_t b_over_a, mb_block* out) {
+    return unary_op(ctx, b_over_a ? mb::EW_RDIV : mb::EW_DIV, A, out, b, 0.0, "divide");
+}
+
+int32_t mb_block_copy(mb_ctx* ctx, const mb_block* A, mb_block* out) {
+    MB_CTX(ctx);
+    if (!A || !out) return fail(MB_ERR_INVALID_ARG, "mb_block_copy: null block");
+    int32_t r = same_shape(A, out, "copy");
+    if (r) return r;
+    return copy_convert(ctx, A, out);
+}
+
+int32_t mb_block_transpose(mb_ctx* ctx, const mb_block* A, mb_block* out) {
+    MB_CTX(ctx);
+    if (!A || !out) return fail(MB_ERR_INVALID_ARG, "mb_block_transpose: null block");
+    if (out->rows != A->cols || out->cols != A->rows)
+        return fail(MB_ERR_DIM_MISMATCH, "transpose: result block is %dx%d, expected %dx%d", out->rows, out->cols, A->cols, A->rows);
+    mb_block view = *A;     // A^T as a view, then materialise it (denseBlock.t.copy)
+    view.owns = 0;
+    std::swap(view.rows, view.cols);
+    view.is_transpose = !A->is_transpose;
+    return copy_convert(ctx, &view, out);
+}
+
+int32_t mb_block_sum(mb_ctx* ctx, const mb_block* A, double* sum_out) {
+    MB_CTX(ctx);
+    if (!A || !sum_out) return fail(MB_ERR_INVALID_ARG, "mb_block_sum: null argument");
+    if (A->dtype != MB_F64) return fail(MB_ERR_UNSUPPORTED, "mb_block_sum: fp64 blocks only");
+    if (A->rows == 0 || A->cols == 0) { *sum_out = 0.0; return MB_OK; }
+    const int minor = A->is_transpose ? A->cols : A->rows, major = A->is_transpose ? A->rows : A->cols;
+    MB_CUDA(mb::sum_f64(f64_ptr(A), minor, major, A->ld, ctx->scratch, ctx->stream));
+    ctx->launches += 2;
+    MB_CUDA(cudaMemcpyAsync(ctx->host_scalar, ctx->scratch, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    MB_CUDA(cudaStreamSynchronize(ctx->stream));
+    *sum_out = *ctx->host_scalar;
+    return MB_OK;
+}
+
+int32_t mb_fill_uniform(mb_ctx* ctx, mb_block* blk, int64_t partition_seed, int64_t first, double lo, double hi,
+                        int32_t row_major) {
+    MB_CTX(ctx);
+    if (!blk || first < 0) return fail(MB_ERR_INVALID_ARG, "mb_fill_uniform: bad argument");
+    if (blk->dtype != MB_F64) return fail(MB_ERR_UNSUPPORTED, "mb_fill_uniform: fp64 blocks only (convert afterwards)");
+    // generator.setSeed(partition.seed) -> XORShiftRandom.setSeed -> seed = hashSeed(s)
+    const unsigned long long state0 = (unsigned long long)mb_hash_seed(partition_seed);
+    MB_CUDA(mb::fill_uniform_f64(f64_ptr(blk), rs(blk), cs(blk), blk->rows, blk->cols, row_major ? 1 : 0, state0, first, lo,
+                                 hi, ctx->stream));
+    ctx->launches++;
+    return MB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,457 @@
+// HBM-bound block kernels: add / subtract / scalar ops / Hadamard / transpose / copy / sum and the
+// on-device XORShift input generator.  All of these stream each element once, so the design is
+// 128-bit vectorised global accesses, enough bytes in flight per SM, no shared memory except for
+// the transpose (which needs it to make both the load and the store side coalesced).
+//
+// Reference semantics: matrix/SubMatrix.scala:41-85,123-131 (Breeze + - / * on BDM),
+// matrix/BlockMatrix.scala:414-452 (subtractBy/divideBy), :467-472 (sum), :494-500 (dotProduct =
+// Hadamard), :514-523 (transpose = denseBlock.t.copy), utils/RandomDataGenerator.scala:53-65,113-131.
+#include "elementwise.h"
+#include "ptx.cuh"
+#include <cuda_bf16.h>
+
+namespace mb {
+
+namespace {
+
+constexpr int EW_THREADS = 256;
+
+__device__ __forceinline__ double apply_bin(int op, double a, double b) {
+    switch (op) {
+        case EW_ADD: return __dadd_rn(a, b);
+        case EW_SUB: return __dsub_rn(a, b);
+        default: return __dmul_rn(a, b);
+    }
+}
+// alpha*a + beta with two roundings (the JVM never fuses); EW_DIV: a / s ; EW_RDIV: s / a
+__device__ __forceinline__ double apply_un(int op, double a, double alpha, double beta) {
+    switch (op) {
+        case EW_AXPB: return __dadd_rn(__dmul_rn(alpha, a), beta);
+        case EW_DIV: return __ddiv_rn(a, alpha);
+        case EW_RDIV: return __ddiv_rn(alpha, a);
+        default: return a;
+    }
+}
+
+// ---- flat (packed, same orientation) fast paths: 128-bit accesses, 4 independent loads in flight ----
+template <int OP>
+__global__ void __launch_bounds__(EW_THREADS) binary_flat_kernel(const double2* __restrict__ a,
+                                                                const double2* __restrict__ b,
+                                                                double2* __restrict__ o, long long n2) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    for (; i + 3 * stride < n2; i += 4 * stride) {
+        double2 x[4], y[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { x[u] = __ldg(a + i + u * stride); y[u] = __ldg(b + i + u * stride); }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            o[i + u * stride] = make_double2(apply_bin(OP, x[u].x, y[u].x), apply_bin(OP, x[u].y, y[u].y));
+    }
+    for (; i < n2; i += stride) {
+        const double2 x = __ldg(a + i), y = __ldg(b + i);
+        o[i] = make_double2(apply_bin(OP, x.x, y.x), apply_bin(OP, x.y, y.y));
+    }
+}
+
+template <int OP>
+__global__ void __launch_bounds__(EW_THREADS) unary_flat_kernel(const double2* __restrict__ a, double2* __restrict__ o,
+                                                               long long n2, double alpha, double beta) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    for (; i + 3 * stride < n2; i += 4 * stride) {
+        double2 x[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) x[u] = __ldg(a + i + u * stride);
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            o[i + u * stride] = make_double2(apply_un(OP, x[u].x, alpha, beta), apply_un(OP, x[u].y, alpha, beta));
+    }
+    for (; i < n2; i += stride) {
+        const double2 x = __ldg(a + i);
+        o[i] = make_double2(apply_un(OP, x.x, alpha, beta), apply_un(OP, x.y, alpha, beta));
+    }
+}
+
+// ---- general strided path (views with ld != rows, odd sizes, mixed orientation) ----
+// element (r,c) of a view: base[r*rs + c*cs]
+__global__ void binary_strided_kernel(int op, int rows, int cols, const double* a, long long ars, long long acs,
+                                      const double* b, long long brs, long long bcs, double* o, long long ors,
+                                      long long ocs) {
+    const long long total = (long long)rows * cols;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
+         e += (long long)gridDim.x * blockDim.x) {
+        const long long r = e % rows, c = e / rows;
+        const double x = a[r * ars + c * acs], y = b[r * brs + c * bcs];
+        o[r * ors + c * ocs] = (op == EW_ADD) ? __dadd_rn(x, y) : (op == EW_SUB) ? __dsub_rn(x, y) : __dmul_rn(x, y);
+    }
+}
+__global__ void unary_strided_kernel(int op, int rows, int cols, const double* a, long long ars, long long acs,
+                                     double* o, long long ors, long long ocs, double alpha, double beta) {
+    const long long total = (long long)rows * cols;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
+         e += (long long)gridDim.x * blockDim.x) {
+        const long long r = e % rows, c = e / rows;
+        const double x = a[r * ars + c * acs];
+        double v;
+        if (op == EW_AXPB) v = __dadd_rn(__dmul_rn(alpha, x), beta);
+        else if (op == EW_DIV) v = __ddiv_rn(x, alpha);
+        else if (op == EW_RDIV) v = __ddiv_rn(alpha, x);
+        else v = x;
+        o[r * ors + c * ocs] = v;
+    }
+}
+
+// ---- transpose: out (cols x rows, ldo) = in (rows x cols, ldi)^T, both column-major ----
+// 64x64 tile = 32x32 micro-blocks of 2x2 doubles.  Each thread loads a 2x2 micro-block with two
+// 128-bit loads (two adjacent columns), transposes it in registers, parks it in shared memory and a
+// different thread writes it with two 128-bit stores, so both HBM directions are fully coalesced.
+// Shared-memory slot of 16B unit (rb, cb, half):  rb*64 + 16*(cb>>3) + 8*half + ((cb&7) ^ (rb&7))
+// which is conflict-free for the column-wise writes and the row-wise reads.
+constexpr int TT = 64;
+__global__ void __launch_bounds__(256) transpose_f64_tile_kernel(const double* __restrict__ in, long long ldi,
+                                                                double* __restrict__ out, long long ldo, int rows,
+                                                                int cols) {
+    __shared__ double2 tile[32 * 64];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int r0 = blockIdx.x * TT, c0 = blockIdx.y * TT;
+    // load phase: lane -> micro-row rb, warp -> micro-cols cb = warp + 8*i
+    {
+        const int rb = lane;
+        const int r = r0 + 2 * rb;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int cb = warp + 8 * i;
+            const int c = c0 + 2 * cb;
+            double2 v0 = make_double2(0.0, 0.0), v1 = v0;
+            if (r < rows && c < cols) {   // rows, cols even -> whole micro-block in range
+                v0 = __ldg(reinterpret_cast<const double2*>(in + r + (long long)c * ldi));
+                v1 = __ldg(reinterpret_cast<const double2*>(in + r + (long long)(c + 1) * ldi));
+            }
+            const int base = rb * 64 + 16 * (cb >> 3) + ((cb & 7) ^ (rb & 7));
+            tile[base] = make_double2(v0.x, v1.x);       // out column r   : in(r, c), in(r, c+1)
+            tile[base + 8] = make_double2(v0.y, v1.y);   // out column r+1 : in(r+1, c), in(r+1, c+1)
+        }
+    }
+    __syncthreads();
+    {
+        const int cb = lane;
+        const int c = c0 + 2 * cb;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int rb = warp + 8 * i;
+            const int r = r0 + 2 * rb;
+            if (r < rows && c < cols) {
+                const int base = rb * 64 + 16 * (cb >> 3) + ((cb & 7) ^ (rb & 7));
+                *reinterpret_cast<double2*>(out + c + (long long)r * ldo) = tile[base];
+                *reinterpret_cast<double2*>(out + c + (long long)(r + 1) * ldo) = tile[base + 8];
+            }
+        }
+    }
+}
+
+// generic transpose (any alignment / odd sizes / any element type): 32x32 tile, scalar accesses
+template <typename T>
+__global__ void __launch_bounds__(256) transpose_generic_kernel(const T* __restrict__ in, long long ldi,
+                                                               T* __restrict__ out, long long ldo, int rows, int cols) {
+    __shared__ T tile[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int r0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int r = r0 + tx, c = c0 + ty + 8 * i;
+        if (r < rows && c < cols) tile[ty + 8 * i][tx] = in[r + (long long)c * ldi];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int c = c0 + tx, r = r0 + ty + 8 * i;
+        if (r < rows && c < cols) out[c + (long long)r * ldo] = tile[tx][ty + 8 * i];
+    }
+}
+
+// ---- sum: two-stage deterministic tree (fixed grid => run-to-run reproducible) ----
+constexpr int SUM_BLOCKS = 148 * 4;
+__device__ __forceinline__ double block_reduce_sum(double v) {
+    __shared__ double warp_part[8];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) warp_part[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double t = 0.0;
+    if (threadIdx.x < 8) t = warp_part[threadIdx.x];
+    if (threadIdx.x < 32) {
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    }
+    return t;
+}
+__global__ void __launch_bounds__(256) sum_strided_kernel(const double* __restrict__ a, int rows, int cols,
+                                                         long long ld, double* __restrict__ partial) {
+    const long long total = (long long)rows * cols;
+    double s0 = 0.0, s1 = 0.0;
+    const bool packed_vec = (ld == rows) && ((reinterpret_cast<uintptr_t>(a) & 15) == 0);
+    if (packed_vec) {
+        const long long n2 = total >> 1;
+        const double2* a2 = reinterpret_cast<const double2*>(a);
+        for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n2;
+             i += (long long)gridDim.x * blockDim.x) {
+            const double2 v = __ldg(a2 + i);
+            s0 += v.x;
+            s1 += v.y;
+        }
+        if ((total & 1) && blockIdx.x == 0 && threadIdx.x == 0) s0 += a[total - 1];
+    } else {
+        for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
+             e += (long long)gridDim.x * blockDim.x)
+            s0 += a[(e % rows) + (e / rows) * ld];
+    }
+    const double t = block_reduce_sum(s0 + s1);
+    if (threadIdx.x == 0) partial[blockIdx.x] = t;
+}
+__global__ void __launch_bounds__(256) sum_final_kernel(const double* __restrict__ partial, int n, double* out) {
+    double s = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) s += partial[i];
+    const double t = block_reduce_sum(s);
+    if (threadIdx.x == 0) *out = t;
+}
+
+// ---- dtype conversion (fp64 <-> bf16 / fp32), strided views ----
+template <typename TI, typename TO>
+__device__ __forceinline__ TO cvt(TI v);
+template <> __device__ __forceinline__ double cvt<double, double>(double v) { return v; }
+template <> __device__ __forceinline__ __nv_bfloat16 cvt<double, __nv_bfloat16>(double v) { return __double2bfloat16(v); }
+template <> __device__ __forceinline__ float cvt<double, float>(double v) { return __double2float_rn(v); }
+template <> __device__ __forceinline__ double cvt<__nv_bfloat16, double>(__nv_bfloat16 v) { return (double)__bfloat162float(v); }
+template <> __device__ __forceinline__ double cvt<float, double>(float v) { return (double)v; }
+template <> __device__ __forceinline__ __nv_bfloat16 cvt<__nv_bfloat16, __nv_bfloat16>(__nv_bfloat16 v) { return v; }
+template <> __device__ __forceinline__ float cvt<float, float>(float v) { return v; }
+template <> __device__ __forceinline__ float cvt<__nv_bfloat16, float>(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <> __device__ __forceinline__ __nv_bfloat16 cvt<float, __nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+template <typename TI, typename TO>
+__global__ void convert_strided_kernel(int rows, int cols, const TI* a, long long ars, long long acs, TO* o,
+                                       long long ors, long long ocs) {
+    const long long total = (long long)rows * cols;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
+         e += (long long)gridDim.x * blockDim.x) {
+        const long long r = e % rows, c = e / rows;
+        o[r * ors + c * ocs] = cvt<TI, TO>(a[r * ars + c * acs]);
+    }
+}
+
+// ---- XORShift uniform generator (utils/RandomDataGenerator.scala:113-131) ----
+// state' = s ^ (s<<21); ^= (>>>35); ^= (<<4).  The map is GF(2)-linear, so value i of a partition
+// stream is reachable by a jump: state_i = T^(2i) * state_0 (nextDouble consumes two steps).
+// jump[j] holds the 64 columns of T^(2^j); a chunk start is the product of the set bits of 2*first.
+__constant__ unsigned long long c_jump[40][64];
+
+__device__ __forceinline__ unsigned long long xs_step(unsigned long long s) {
+    s ^= s << 21;
+    s ^= s >> 35;
+    s ^= s << 4;
+    return s;
+}
+__device__ unsigned long long xs_jump(unsigned long long s, unsigned long long steps) {
+    for (int j = 0; j < 40 && steps; ++j, steps >>= 1) {
+        if (steps & 1ull) {
+            unsigned long long t = 0;
+            unsigned long long x = s;
+            // t = sum over set bits b of x of column b
+            while (x) {
+                const int b = __ffsll((long long)x) - 1;
+                t ^= c_jump[j][b];
+                x &= x - 1;
+            }
+            s = t;
+        }
+    }
+    return s;
+}
+constexpr int FILL_CHUNK = 128;   // values per thread
+__global__ void __launch_bounds__(256) fill_uniform_kernel(double* out, long long rs, long long cs, int rows, int cols,
+                                                          int row_major, unsigned long long state0, long long first,
+                                                          double lo, double hi) {
+    const long long total = (long long)rows * cols;
+    const long long chunk = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    long long i = chunk * FILL_CHUNK;
+    if (i >= total) return;
+    const long long end = min(total, i + FILL_CHUNK);
+    unsigned long long s = xs_jump(state0, 2ull * (unsigned long long)(first + i));
+    const double span = __dsub_rn(hi, lo);
+    for (; i < end; ++i) {
+        s = xs_step(s);
+        const unsigned long long hi26 = s & ((1ull << 26) - 1);
+        s = xs_step(s);
+        const unsigned long long lo27 = s & ((1ull << 27) - 1);
+        const double u = (double)((hi26 << 27) + lo27) * 0x1.0p-53;
+        const double v = __dadd_rn(__dmul_rn(span, u), lo);
+        long long r, c;
+        if (row_major) { r = i / cols; c = i % cols; } else { c = i / rows; r = i % rows; }
+        out[r * rs + c * cs] = v;
+    }
+}
+
+inline int ew_grid(long long work_items) {
+    long long b = (work_items + EW_THREADS - 1) / EW_THREADS;
+    const long long cap = 148 * 8;   // 8 resident 256-thread blocks per SM
+    if (b > cap) b = cap;
+    if (b < 1) b = 1;
+    return (int)b;
+}
+
+}  // namespace
+
+cudaError_t ew_binary(int op, int rows, int cols, const double* a, long long ars, long long acs, const double* b,
+                      long long brs, long long bcs, double* o, long long ors, long long ocs, cudaStream_t st) {
+    if (rows <= 0 || cols <= 0) return cudaSuccess;
+    const long long total = (long long)rows * cols;
+    const bool packed = ars == 1 && brs == 1 && ors == 1 && acs == rows && bcs == rows && ocs == rows;
+    const bool aligned = ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) |
+                           reinterpret_cast<uintptr_t>(o)) & 15) == 0;
+    if (packed && aligned && (total % 2 == 0)) {
+        const long long n2 = total / 2;
+        const int grid = ew_grid((n2 + 3) / 4);
+        const double2 *a2 = reinterpret_cast<const double2*>(a), *b2 = reinterpret_cast<const double2*>(b);
+        double2* o2 = reinterpret_cast<double2*>(o);
+        if (op == EW_ADD) binary_flat_kernel<EW_ADD><<<grid, EW_THREADS, 0, st>>>(a2, b2, o2, n2);
+        else if (op == EW_SUB) binary_flat_kernel<EW_SUB><<<grid, EW_THREADS, 0, st>>>(a2, b2, o2, n2);
+        else binary_flat_kernel<EW_MUL><<<grid, EW_THREADS, 0, st>>>(a2, b2, o2, n2);
+    } else {
+        binary_strided_kernel<<<ew_grid(total), EW_THREADS, 0, st>>>(op, rows, cols, a, ars, acs, b, brs, bcs, o, ors, ocs);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t ew_unary(int op, int rows, int cols, const double* a, long long ars, long long acs, double* o,
+                     long long ors, long long ocs, double alpha, double beta, cudaStream_t st) {
+    if (rows <= 0 || cols <= 0) return cudaSuccess;
+    const long long total = (long long)rows * cols;
+    const bool packed = ars == 1 && ors == 1 && acs == rows && ocs == rows;
+    const bool aligned = ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(o)) & 15) == 0;
+    if (packed && aligned && (total % 2 == 0)) {
+        const long long n2 = total / 2;
+        const int grid = ew_grid((n2 + 3) / 4);
+        const double2* a2 = reinterpret_cast<const double2*>(a);
+        double2* o2 = reinterpret_cast<double2*>(o);
+        if (op == EW_AXPB) unary_flat_kernel<EW_AXPB><<<grid, EW_THREADS, 0, st>>>(a2, o2, n2, alpha, beta);
+        else if (op == EW_DIV) unary_flat_kernel<EW_DIV><<<grid, EW_THREADS, 0, st>>>(a2, o2, n2, alpha, beta);
+        else if (op == EW_RDIV) unary_flat_kernel<EW_RDIV><<<grid, EW_THREADS, 0, st>>>(a2, o2, n2, alpha, beta);
+        else unary_flat_kernel<EW_COPY><<<grid, EW_THREADS, 0, st>>>(a2, o2, n2, alpha, beta);
+    } else {
+        unary_strided_kernel<<<ew_grid(total), EW_THREADS, 0, st>>>(op, rows, cols, a, ars, acs, o, ors, ocs, alpha, beta);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t transpose_f64(const double* in, long long ldi, double* out, long long ldo, int rows, int cols,
+                          cudaStream_t st) {
+    if (rows <= 0 || cols <= 0) return cudaSuccess;
+    const bool fast = (rows % 2 == 0) && (cols % 2 == 0) && (ldi % 2 == 0) && (ldo % 2 == 0) &&
+                      (((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) == 0);
+    if (fast) {
+        dim3 grid((rows + TT - 1) / TT, (cols + TT - 1) / TT);
+        transpose_f64_tile_kernel<<<grid, 256, 0, st>>>(in, ldi, out, ldo, rows, cols);
+    } else {
+        dim3 grid((rows + 31) / 32, (cols + 31) / 32);
+        transpose_generic_kernel<double><<<grid, 256, 0, st>>>(in, ldi, out, ldo, rows, cols);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t transpose_b16(const void* in, long long ldi, void* out, long long ldo, int rows, int cols, cudaStream_t st) {
+    if (rows <= 0 || cols <= 0) return cudaSuccess;
+    dim3 grid((rows + 31) / 32, (cols + 31) / 32);
+    transpose_generic_kernel<unsigned short><<<grid, 256, 0, st>>>(static_cast<const unsigned short*>(in), ldi,
+                                                                  static_cast<unsigned short*>(out), ldo, rows, cols);
+    return cudaGetLastError();
+}
+cudaError_t transpose_b32(const void* in, long long ldi, void* out, long long ldo, int rows, int cols, cudaStream_t st) {
+    if (rows <= 0 || cols <= 0) return cudaSuccess;
+    dim3 grid((rows + 31) / 32, (cols + 31) / 32);
+    transpose_generic_kernel<unsigned int><<<grid, 256, 0, st>>>(static_cast<const unsigned int*>(in), ldi,
+                                                                static_cast<unsigned int*>(out), ldo, rows, cols);
+    return cudaGetLastError();
+}
+
+int sum_scratch_doubles() { return SUM_BLOCKS + 1; }
+
+cudaError_t sum_f64(const double* a, int rows, int cols, long long ld, double* scratch, cudaStream_t st) {
+    // scratch[0] receives the result, scratch[1..] the per-block partials
+    const long long total = (long long)rows * cols;
+    int blocks = (int)min((long long)SUM_BLOCKS, max(1ll, (total + 511) / 512));
+    sum_strided_kernel<<<blocks, 256, 0, st>>>(a, rows, cols, ld, scratch + 1);
+    sum_final_kernel<<<1, 256, 0, st>>>(scratch + 1, blocks, scratch);
+    return cudaGetLastError();
+}
+
+template <typename TI, typename TO>
+static cudaError_t convert_t(int rows, int cols, const void* a, long long ars, long long acs, void* o, long long ors,
+                             long long ocs, cudaStream_t st) {
+    if (rows <= 0 || cols <= 0) return cudaSuccess;
+    convert_strided_kernel<TI, TO><<<ew_grid((long long)rows * cols), EW_THREADS, 0, st>>>(
+        rows, cols, static_cast<const TI*>(a), ars, acs, static_cast<TO*>(o), ors, ocs);
+    return cudaGetLastError();
+}
+
+// dtype codes follow mb_dtype: 0 = f64, 1 = bf16, 2 = f32
+cudaError_t convert_strided(int src_dtype, int dst_dtype, int rows, int cols, const void* a, long long ars,
+                            long long acs, void* o, long long ors, long long ocs, cudaStream_t st) {
+    using bf = __nv_bfloat16;
+    if (src_dtype == 0 && dst_dtype == 0) return convert_t<double, double>(rows, cols, a, ars, acs, o, ors, ocs, st);
+    if (src_dtype == 0 && dst_dtype == 1) return convert_t<double, bf>(rows, cols, a, ars, acs, o, ors, ocs, st);
+    if (src_dtype == 0 && dst_dtype == 2) return convert_t<double, float>(rows, cols, a, ars, acs, o, ors, ocs, st);
+    if (src_dtype == 1 && dst_dtype == 0) return convert_t<bf, double>(rows, cols, a, ars, acs, o, ors, ocs, st);
+    if (src_dtype == 2 && dst_dtype == 0) return convert_t<float, double>(rows, cols, a, ars, acs, o, ors, ocs, st);
+    if (src_dtype == 1 && dst_dtype == 1) return convert_t<bf, bf>(rows, cols, a, ars, acs, o, ors, ocs, st);
+    if (src_dtype == 2 && dst_dtype == 2) return convert_t<float, float>(rows, cols, a, ars, acs, o, ors, ocs, st);
+    if (src_dtype == 1 && dst_dtype == 2) return convert_t<bf, float>(rows, cols, a, ars, acs, o, ors, ocs, st);
+    if (src_dtype == 2 && dst_dtype == 1) return convert_t<float, bf>(rows, cols, a, ars, acs, o, ors, ocs, st);
+    return cudaErrorInvalidValue;
+}
+
+// ---- XORShift jump tables (host) ----
+static unsigned long long h_step(unsigned long long s) {
+    s ^= s << 21;
+    s ^= s >> 35;
+    s ^= s << 4;
+    return s;
+}
+cudaError_t fill_uniform_init_tables() {
+    static bool done[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && done[dev]) return cudaSuccess;
+    static unsigned long long tab[40][64];
+    static bool built = false;
+    if (!built) {
+        // column b of T^1 = step(1<<b); T^(2^(j+1)) = T^(2^j) applied to the columns of T^(2^j)
+        for (int b = 0; b < 64; ++b) tab[0][b] = h_step(1ull << b);
+        for (int j = 1; j < 40; ++j) {
+            for (int b = 0; b < 64; ++b) {
+                unsigned long long x = tab[j - 1][b], t = 0;
+                for (int c = 0; c < 64; ++c)
+                    if ((x >> c) & 1ull) t ^= tab[j - 1][c];
+                tab[j][b] = t;
+            }
+        }
+        built = true;
+    }
+    cudaError_t e = cudaMemcpyToSymbol(c_jump, tab, sizeof(tab));
+    if (e == cudaSuccess && dev >= 0 && dev < 64) done[dev] = true;
+    return e;
+}
+
+cudaError_t fill_uniform_f64(double* out, long long rs, long long cs, int rows, int cols, int row_major,
+                             unsigned long long state0, long long first, double lo, double hi, cudaStream_t st) {
+    if (rows <= 0 || cols <= 0) return cudaSuccess;
+    cudaError_t e = fill_uniform_init_tables();
+    if (e != cudaSuccess) return e;
+    const long long total = (long long)rows * cols;
+    const long long chunks = (total + FILL_CHUNK - 1) / FILL_CHUNK;
+    const int blocks = (int)((chunks + 255) / 256);
+    fill_uniform_kernel<<<blocks, 256, 0, st>>>(out, rs, cs, rows, cols, row_major, state0, first, lo, hi);
+    return cudaGetLastError();
+}
+
+}  // namespace mb

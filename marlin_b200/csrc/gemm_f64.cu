@@ -1,0 +1,422 @@
+// fp64 block GEMM for sm_100a — replaces SubMatrix.multiply -> Breeze `*` -> netlib dgemm
+// (reference: matrix/SubMatrix.scala:87-91; inline twins matrix/DenseVecMatrix.scala:122,129,1676).
+//
+// tcgen05.mma has no .kind::f64 (ptxas rejects it), so the fp64 tensor-core path on B200 is
+// DMMA (mma.sync.m8n8k4.f64 -> SASS DMMA.8x8x4).  Design:
+//   * persistent CTAs (one per SM), 128x128 C tile per CTA, accumulators in registers
+//     (8 consumer warps x 64x32 warp tile = 64 doubles / thread);
+//   * a dedicated producer warp streams A/B k-slabs (BK = 16) through a 6-stage shared-memory
+//     ring with TMA (cp.async.bulk.tensor.2d, SWIZZLE_128B) + mbarrier full/empty pairs;
+//     TMA zero-fills out-of-range rows/cols, so ragged blocks (ceil-sized last block of
+//     BlockMatrix, matrix/BlockMatrix.scala:73-74) need no host-side padding;
+//   * operand fragments are read with conflict-free 128-bit LDS from the swizzled tiles: the
+//     MMA row/col and k slots are permuted (any permutation of the m, n, k index sets is a valid
+//     GEMM as long as A, B and C agree) so that every quarter-warp hits 8 distinct 16B chunks;
+//   * setmaxnreg moves registers from the producer warpgroup to the two consumer warpgroups.
+//
+// Both operands may be 'N' or 'T' (Breeze isTranspose views): an operand whose contiguous
+// dimension is M/N ("MN form") is staged as 8 boxes of [16 k-rows][16 mn] and one whose
+// contiguous dimension is K ("K form") as one box of [128 mn-rows][16 k].
+#include "gemm_f64.h"
+#include "ptx.cuh"
+
+namespace mb {
+
+namespace {
+
+constexpr int BM = 128, BN = 128, BK = 16;
+constexpr int OPERAND_BYTES = BM * BK * 8;          // 16 KiB per operand per stage
+constexpr int STAGE_BYTES = 2 * OPERAND_BYTES;      // 32 KiB
+constexpr int NUM_STAGES = 6;                       // 192 KiB ring
+constexpr int NUM_CONSUMER_WARPS = 8;
+constexpr int NUM_THREADS = 128 + NUM_CONSUMER_WARPS * 32;   // producer warpgroup + 2 consumer warpgroups
+constexpr int SMEM_BYTES = NUM_STAGES * STAGE_BYTES + 2 * NUM_STAGES * 8 + 1024;
+constexpr int BAND = 16;                            // tile-rows per rasterisation band (L2 reuse)
+
+struct Params {
+    int M, N, K;
+    double alpha, beta;
+    double* C;
+    long long ldc;
+    int tiles_m, tiles_n;
+};
+
+__device__ __forceinline__ int perm8(int r) { return ((r & 1) << 2) | (r >> 1); }
+
+// tile id -> (tile_m, tile_n): bands of BAND tile-rows, column-major inside a band, so the ~148
+// tiles in flight cover a BAND x (148/BAND) patch and share A row-panels / B column-panels in L2.
+__device__ __forceinline__ void tile_coords(int t, int tiles_m, int tiles_n, int& tm, int& tn) {
+    const int band_tiles = BAND * tiles_n;
+    const int band = t / band_tiles;
+    const int r = t - band * band_tiles;
+    const int rows_in_band = min(BAND, tiles_m - band * BAND);
+    tn = r / rows_in_band;
+    tm = band * BAND + (r - tn * rows_in_band);
+}
+
+template <bool TA, bool TB>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_f64_dmma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+                     const Params p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bar_full = smem_base + NUM_STAGES * STAGE_BYTES;
+    const uint32_t bar_empty = bar_full + NUM_STAGES * 8;
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int num_tiles = p.tiles_m * p.tiles_n;
+    const int num_kb = (p.K + BK - 1) / BK;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NUM_STAGES; ++s) {
+            mbar_init(bar_full + 8 * s, 1);
+            mbar_init(bar_empty + 8 * s, NUM_CONSUMER_WARPS);
+        }
+        fence_barrier_init();
+        tma_prefetch_desc(&mapA);
+        tma_prefetch_desc(&mapB);
+    }
+    __syncthreads();
+
+    if (warp < 4) {
+        // ===================== producer warpgroup =====================
+        setmaxnreg_dec<40>();
+        if (warp == 0 && lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+                int tm, tn;
+                tile_coords(t, p.tiles_m, p.tiles_n, tm, tn);
+                const int m0 = tm * BM, n0 = tn * BN;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+                    const uint32_t full = bar_full + 8 * stage;
+                    const uint32_t sA = smem_base + stage * STAGE_BYTES;
+                    const uint32_t sB = sA + OPERAND_BYTES;
+                    mbar_arrive_expect_tx(full, STAGE_BYTES);
+                    const int k0 = kb * BK;
+                    if (!TA) {
+#pragma unroll
+                        for (int b = 0; b < 8; ++b) tma_load_2d(sA + b * 2048, &mapA, full, m0 + 16 * b, k0);
+                    } else {
+                        tma_load_2d(sA, &mapA, full, k0, m0);
+                    }
+                    if (!TB) {
+                        tma_load_2d(sB, &mapB, full, k0, n0);
+                    } else {
+#pragma unroll
+                        for (int b = 0; b < 8; ++b) tma_load_2d(sB + b * 2048, &mapB, full, n0 + 16 * b, k0);
+                    }
+                    if (++stage == NUM_STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+        return;
+    }
+
+    // ========================= consumer warpgroups =========================
+    setmaxnreg_inc<232>();
+    const int cw = warp - 4;          // 0..7
+    const int warp_m = cw & 1;        // 64-row slab
+    const int warp_n = cw >> 1;       // 32-col slab
+    const int r = lane >> 2;          // MMA row (A) / col (B) index of this lane
+    const int q = lane & 3;           // MMA k slot of this lane
+    const int pr = perm8(r);
+
+    // Per-lane byte offsets of the fragment loads inside one operand tile (see header comment).
+    //  MN form: box t' (16 mn x 16 k, 2 KiB), k-row = 8h + 2q + p, 16B chunk = r ^ ((2q+p)&7)
+    //           -> doubles (mn = 16t' + 2r, 16t' + 2r + 1)  = MMA tiles 2t', 2t'+1, row r.
+    //  K  form: row mn = base + 8u + perm8(r), 16B chunk = (4h + q) ^ perm8(r)
+    //           -> doubles (k = 8h + 2q, 8h + 2q + 1)       = phases p = 0, 1.
+    uint32_t offA[2][2], offB[2][2];   // [h][p] for MN form, [h][0] used for K form
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+#pragma unroll
+        for (int pp = 0; pp < 2; ++pp) {
+            const int krow = 8 * h + 2 * q + pp;
+            const uint32_t mn_off = krow * 128 + ((r ^ (krow & 7)) << 4);
+            const uint32_t k_off = pr * 128 + ((((4 * h + q) ^ pr) & 7) << 4);
+            offA[h][pp] = !TA ? (warp_m * 4 * 2048 + mn_off) : (warp_m * 64 * 128 + k_off);
+            offB[h][pp] = TB ? (warp_n * 2 * 2048 + mn_off) : (warp_n * 32 * 128 + k_off);
+        }
+    }
+
+    int stage = 0;
+    uint32_t phase = 0;
+    const bool vec_ok = ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) && ((p.ldc & 1) == 0);
+
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        int tm_, tn_;
+        tile_coords(t, p.tiles_m, p.tiles_n, tm_, tn_);
+        const int m0 = tm_ * BM, n0 = tn_ * BN;
+
+        double acc[8][4][2];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+        for (int kb = 0; kb < num_kb; ++kb) {
+            mbar_wait(bar_full + 8 * stage, phase);
+            const uint32_t sA = smem_base + stage * STAGE_BYTES;
+            const uint32_t sB = sA + OPERAND_BYTES;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                double a[8][2];   // [m-tile][phase]
+                double b[4][2];   // [n-tile][phase]
+                if (!TA) {
+#pragma unroll
+                    for (int tp = 0; tp < 4; ++tp)
+#pragma unroll
+                        for (int pp = 0; pp < 2; ++pp)
+                            lds128(a[2 * tp][pp], a[2 * tp + 1][pp], sA + offA[h][pp] + tp * 2048);
+                } else {
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) lds128(a[u][0], a[u][1], sA + offA[h][0] + u * 8 * 128);
+                }
+                if (!TB) {
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) lds128(b[u][0], b[u][1], sB + offB[h][0] + u * 8 * 128);
+                } else {
+#pragma unroll
+                    for (int tp = 0; tp < 2; ++tp)
+#pragma unroll
+                        for (int pp = 0; pp < 2; ++pp)
+                            lds128(b[2 * tp][pp], b[2 * tp + 1][pp], sB + offB[h][pp] + tp * 2048);
+                }
+                if (h == 1) {
+                    // all reads of this stage are issued; hand the slot back to the producer
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_empty + 8 * stage);
+                }
+#pragma unroll
+                for (int pp = 0; pp < 2; ++pp)
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], a[i][pp], b[j][pp]);
+            }
+            if (++stage == NUM_STAGES) { stage = 0; phase ^= 1; }
+        }
+
+        // ---------------- epilogue: C = alpha*acc + beta*C ----------------
+        // lane holds C[mrow(i-tile, r)][ncol(j-tile, 2q + jj)]
+        const double alpha = p.alpha, beta = p.beta;
+        const bool use_beta = (beta != 0.0);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+#pragma unroll
+            for (int jj = 0; jj < 2; ++jj) {
+                const int cj = 2 * q + jj;
+                const int n = n0 + warp_n * 32 + (!TB ? (8 * j + perm8(cj)) : (16 * (j >> 1) + 2 * cj + (j & 1)));
+                if (n >= p.N) continue;
+                double* ccol = p.C + (long long)n * p.ldc;
+                if (!TA) {
+#pragma unroll
+                    for (int tp = 0; tp < 4; ++tp) {
+                        const int m = m0 + warp_m * 64 + 16 * tp + 2 * r;
+                        if (m >= p.M) continue;
+                        double v0 = alpha * acc[2 * tp][j][jj];
+                        double v1 = alpha * acc[2 * tp + 1][j][jj];
+                        if (vec_ok && m + 1 < p.M) {
+                            double2* ptr = reinterpret_cast<double2*>(ccol + m);
+                            if (use_beta) {
+                                const double2 old = *ptr;
+                                v0 += beta * old.x;
+                                v1 += beta * old.y;
+                            }
+                            *ptr = make_double2(v0, v1);
+                        } else {
+                            if (use_beta) v0 += beta * ccol[m];
+                            ccol[m] = v0;
+                            if (m + 1 < p.M) {
+                                if (use_beta) v1 += beta * ccol[m + 1];
+                                ccol[m + 1] = v1;
+                            }
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int m = m0 + warp_m * 64 + 8 * i + pr;
+                        if (m >= p.M) continue;
+                        double v = alpha * acc[i][j][jj];
+                        if (use_beta) v += beta * ccol[m];
+                        ccol[m] = v;
+                    }
+                }
+            }
+        }
+    }
+}
+
+// -------------------------------------------------------------------------------------------
+// Generic CUDA-core kernel: any ld / offset / alignment, any trans.  64x64 tile, 4x4 per thread.
+// Used when TMA's 16-byte rules do not hold (odd leading dimension or odd element offset of a
+// Breeze view) and as an independent on-device cross-check in the tests.
+// -------------------------------------------------------------------------------------------
+template <bool TA, bool TB>
+__global__ void __launch_bounds__(256)
+gemm_f64_generic_kernel(int M, int N, int K, double alpha, const double* __restrict__ A, long long lda,
+                        const double* __restrict__ B, long long ldb, double beta, double* __restrict__ C,
+                        long long ldc) {
+    constexpr int T = 64, KK = 16;
+    __shared__ double sA[KK][T + 1];
+    __shared__ double sB[KK][T + 1];
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const int m0 = blockIdx.x * T, n0 = blockIdx.y * T;
+    double acc[4][4] = {};
+    for (int k0 = 0; k0 < K; k0 += KK) {
+        for (int e = threadIdx.x; e < T * KK; e += 256) {
+            // A tile element (m, k)
+            int mm, kk;
+            if (!TA) { mm = e % T; kk = e / T; } else { kk = e % KK; mm = e / KK; }
+            const int gm = m0 + mm, gk = k0 + kk;
+            double v = 0.0;
+            if (gm < M && gk < K) v = !TA ? A[gm + (long long)gk * lda] : A[gk + (long long)gm * lda];
+            sA[kk][mm] = v;
+            int nn, kb;
+            if (!TB) { kb = e % KK; nn = e / KK; } else { nn = e % T; kb = e / T; }
+            const int gn = n0 + nn, gk2 = k0 + kb;
+            double w = 0.0;
+            if (gn < N && gk2 < K) w = !TB ? B[gk2 + (long long)gn * ldb] : B[gn + (long long)gk2 * ldb];
+            sB[kb][nn] = w;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < KK; ++kk) {
+            double a[4], b[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) a[i] = sA[kk][tx + 16 * i];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) b[j] = sB[kk][ty + 16 * j];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int n = n0 + ty + 16 * j;
+        if (n >= N) continue;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int m = m0 + tx + 16 * i;
+            if (m >= M) continue;
+            double v = alpha * acc[i][j];
+            double* c = C + m + (long long)n * ldc;
+            if (beta != 0.0) v += beta * *c;
+            *c = v;
+        }
+    }
+}
+
+__global__ void scale_matrix_kernel(int M, int N, double beta, double* C, long long ldc) {
+    const long long total = (long long)M * N;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
+         e += (long long)gridDim.x * blockDim.x) {
+        const long long m = e % M, n = e / M;
+        double* c = C + m + n * ldc;
+        *c = (beta == 0.0) ? 0.0 : beta * *c;
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    }
+    return fn;
+}
+
+// 2-D fp64 tensor map over a column-major array: dim0 (contiguous) x dim1 (stride ld), 128B swizzle.
+bool make_map_f64(CUtensorMap* map, const double* base, uint64_t dim0, uint64_t dim1, uint64_t ld,
+                  uint32_t box0, uint32_t box1) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return false;
+    cuuint64_t dims[2] = {dim0, dim1};
+    cuuint64_t strides[1] = {ld * 8};
+    cuuint32_t box[2] = {box0, box1};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
+template <bool TA, bool TB>
+cudaError_t launch_dmma(const CUtensorMap& mA, const CUtensorMap& mB, const Params& p, int num_sms,
+                        cudaStream_t stream) {
+    auto kern = gemm_f64_dmma_kernel<TA, TB>;
+    static bool attr_done = false;   // per template instantiation
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+        attr_done = true;
+    }
+    const int grid = min(p.tiles_m * p.tiles_n, num_sms);
+    kern<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(mA, mB, p);
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+bool gemm_f64_tma_eligible(const double* A, long long lda, const double* B, long long ldb) {
+    return ((reinterpret_cast<uintptr_t>(A) & 15) == 0) && ((reinterpret_cast<uintptr_t>(B) & 15) == 0) &&
+           (lda % 2 == 0) && (ldb % 2 == 0) && get_encode_fn() != nullptr;
+}
+
+cudaError_t gemm_f64(bool transA, bool transB, int M, int N, int K, double alpha, const double* A, long long lda,
+                     const double* B, long long ldb, double beta, double* C, long long ldc, int num_sms,
+                     cudaStream_t stream, bool force_generic, int* launches) {
+    if (M <= 0 || N <= 0) return cudaSuccess;
+    if (K <= 0 || alpha == 0.0) {
+        if (beta == 1.0) return cudaSuccess;
+        scale_matrix_kernel<<<min(1184, (int)(((long long)M * N + 255) / 256)), 256, 0, stream>>>(M, N, beta, C, ldc);
+        if (launches) ++*launches;
+        return cudaGetLastError();
+    }
+    if (!force_generic && gemm_f64_tma_eligible(A, lda, B, ldb)) {
+        CUtensorMap mA, mB;
+        bool ok = true;
+        // A: 'N' -> stored M x K (m contiguous), MN form boxes [16 m][16 k]; 'T' -> stored K x M, K form box [16 k][128 m]
+        ok = ok && (!transA ? make_map_f64(&mA, A, M, K, lda, 16, 16) : make_map_f64(&mA, A, K, M, lda, 16, 128));
+        // B: 'N' -> stored K x N (k contiguous), K form box [16 k][128 n]; 'T' -> stored N x K, MN form boxes [16 n][16 k]
+        ok = ok && (!transB ? make_map_f64(&mB, B, K, N, ldb, 16, 128) : make_map_f64(&mB, B, N, K, ldb, 16, 16));
+        if (ok) {
+            Params p;
+            p.M = M; p.N = N; p.K = K; p.alpha = alpha; p.beta = beta; p.C = C; p.ldc = ldc;
+            p.tiles_m = (M + BM - 1) / BM;
+            p.tiles_n = (N + BN - 1) / BN;
+            if (launches) ++*launches;
+            if (!transA && !transB) return launch_dmma<false, false>(mA, mB, p, num_sms, stream);
+            if (transA && !transB) return launch_dmma<true, false>(mA, mB, p, num_sms, stream);
+            if (!transA && transB) return launch_dmma<false, true>(mA, mB, p, num_sms, stream);
+            return launch_dmma<true, true>(mA, mB, p, num_sms, stream);
+        }
+    }
+    dim3 grid((M + 63) / 64, (N + 63) / 64);
+    if (launches) ++*launches;
+    if (!transA && !transB)
+        gemm_f64_generic_kernel<false, false><<<grid, 256, 0, stream>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
+    else if (transA && !transB)
+        gemm_f64_generic_kernel<true, false><<<grid, 256, 0, stream>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
+    else if (!transA && transB)
+        gemm_f64_generic_kernel<false, true><<<grid, 256, 0, stream>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
+    else
+        gemm_f64_generic_kernel<true, true><<<grid, 256, 0, stream>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
+    return cudaGetLastError();
+}
+
+}  // namespace mb
