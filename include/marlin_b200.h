@@ -50,8 +50,11 @@ int32_t     mb_init(int32_t device, mb_ctx** out);
 int32_t     mb_shutdown(mb_ctx* ctx);
 const char* mb_last_error(void);
 const char* mb_version(void);
-/* Use an externally owned stream (e.g. torch's current stream) for every later call; 0 = own stream. */
+/* Use an externally owned stream (e.g. torch's current stream) for every later call.  The handle is
+ * used as CUDA would: NULL is the legacy default stream.  mb_reset_stream returns to the ctx's own
+ * (non-blocking) stream, which is what a fresh ctx uses. */
 int32_t     mb_set_stream(mb_ctx* ctx, void* cuda_stream);
+int32_t     mb_reset_stream(mb_ctx* ctx);
 int32_t     mb_synchronize(mb_ctx* ctx);
 /* Number of kernels this library has launched on ctx since init (bench.py's gpu_launches). */
 int64_t     mb_launch_count(mb_ctx* ctx);

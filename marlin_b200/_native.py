@@ -36,6 +36,7 @@ SIGNATURES = {
     "mb_last_error": (C.c_char_p, []),
     "mb_version": (C.c_char_p, []),
     "mb_set_stream": (c_i32, [c_ctx, C.c_void_p]),
+    "mb_reset_stream": (c_i32, [c_ctx]),
     "mb_synchronize": (c_i32, [c_ctx]),
     "mb_launch_count": (c_i64, [c_ctx]),
     "mb_timer_start": (c_i32, [c_ctx]),

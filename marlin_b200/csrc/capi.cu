@@ -204,7 +204,13 @@ int32_t mb_shutdown(mb_ctx* ctx) {
 
 int32_t mb_set_stream(mb_ctx* ctx, void* cuda_stream) {
     if (!ctx) return fail(MB_ERR_INVALID_ARG, "null context");
-    ctx->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->own_stream;
+    ctx->stream = static_cast<cudaStream_t>(cuda_stream);
+    return MB_OK;
+}
+
+int32_t mb_reset_stream(mb_ctx* ctx) {
+    if (!ctx) return fail(MB_ERR_INVALID_ARG, "null context");
+    ctx->stream = ctx->own_stream;
     return MB_OK;
 }
 

@@ -1,0 +1,696 @@
+"""CPU restatement of PasaLab/marlin's dense multiply / transpose / add path (numpy + a small C core).
+
+TEST INFRASTRUCTURE ONLY.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+`--impl reference` legs may import this package; the product (marlin_b200/) never does.
+
+It restates the *algorithm* of the reference, RDD semantics included, on plain Python containers:
+an RDD[(BlockID, SubMatrix)] is a list of ((row, col), ndarray) pairs (Fortran-ordered float64,
+Breeze's column-major DenseMatrix), an RDD[(Long, BDV)] is a list of (index, 1-D ndarray) pairs.
+Every function cites the reference lines it follows (paths relative to
+/root/reference/src/main/scala/edu/nju/pasalab/marlin/).
+
+Arithmetic backends (`gemm=`):
+  "f2j"  — oracle/marlin_oracle.c: reference-BLAS dgemm loop order, no FMA (netlib-java's default
+           pure-Java F2J backend, README.md:31).  Use for small cases.
+  "blas" — numpy matmul (OpenBLAS dgemm, all host threads): netlib-java with native BLAS installed.
+           Use for large cases and for the timed CPU baseline.
+Parity status: pinned against the reference's own golden vectors (DistributedMatrixSuite.scala) in
+tests/test_oracle_golden.py — all exact small integers.  For non-integer fp64 data and for the random
+generator the reference holds no golden vectors => "parity unpinned" for those.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import re
+import subprocess
+from pathlib import Path
+from typing import Dict, Iterable, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+_HERE = Path(__file__).resolve().parent
+_SO = _HERE / "_build" / "libmarlin_oracle.so"
+_lib = None
+
+
+def build(force: bool = False) -> Path:
+    """gcc the C core (see oracle/Makefile). -ffp-contract=off: the JVM never fuses multiply-add."""
+    src = _HERE / "marlin_oracle.c"
+    if force or not _SO.exists() or _SO.stat().st_mtime < src.stat().st_mtime:
+        subprocess.run(["make", "-s", "-C", str(_HERE)], check=True)
+    return _SO
+
+
+def clib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        build()
+        lib = C.CDLL(str(_SO))
+        dp = C.POINTER(C.c_double)
+        lib.mo_dgemm_f2j.restype = C.c_int
+        lib.mo_dgemm_f2j.argtypes = [C.c_char, C.c_char, C.c_int, C.c_int, C.c_int, C.c_double, dp, C.c_long, C.c_int,
+                                     dp, C.c_long, C.c_int, C.c_double, dp, C.c_long, C.c_int]
+        lib.mo_binary.argtypes = [C.c_int, C.c_long, dp, dp, dp]
+        lib.mo_transpose_copy.argtypes = [C.c_int, C.c_int, dp, C.c_long, dp]
+        lib.mo_hash_seed.restype = C.c_int64
+        lib.mo_hash_seed.argtypes = [C.c_int64]
+        lib.mo_uniform_fill.argtypes = [C.c_int64, C.c_long, C.c_long, C.c_double, C.c_double, dp]
+        lib.mo_java_random_longs.argtypes = [C.c_int64, C.c_int, C.POINTER(C.c_int64)]
+        lib.mo_split_method.argtypes = [C.c_int64, C.c_int64, C.c_int64, C.c_int, C.POINTER(C.c_int)]
+        _lib = lib
+    return _lib
+
+
+def _dp(a: np.ndarray):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _f(a) -> np.ndarray:
+    return np.asfortranarray(a, dtype=np.float64)
+
+
+# --------------------------------------------------------------------------------------------
+# Local block kernels (L2 in SURVEY.md): SubMatrix.multiply / add / ... on Breeze BDM[Double]
+# --------------------------------------------------------------------------------------------
+def dgemm_f2j(transa: str, transb: str, m: int, n: int, k: int, alpha: float, a: np.ndarray, a_off: int, lda: int,
+              b: np.ndarray, b_off: int, ldb: int, beta: float, c: np.ndarray, c_off: int, ldc: int) -> None:
+    """netlib BLAS.dgemm on flat double arrays (the third-party seam of SURVEY §8b-1)."""
+    info = clib().mo_dgemm_f2j(transa.encode(), transb.encode(), m, n, k, alpha, _dp(a), a_off, lda, _dp(b), b_off, ldb,
+                               beta, _dp(c), c_off, ldc)
+    if info:
+        raise ValueError(f"dgemm: illegal argument {info}")
+
+
+def block_multiply(a: np.ndarray, b: np.ndarray, gemm: str = "f2j") -> np.ndarray:
+    """SubMatrix.multiply (matrix/SubMatrix.scala:87-91): `denseBlock * other.denseBlock` -> Breeze ->
+    dgemm(transString(a), transString(b), a.rows, b.cols, a.cols, 1.0, a.data, a.offset, a.majorStride, ...,
+    0.0, c.data, 0, c.rows).  A numpy array that is C-contiguous plays the role of an isTranspose view."""
+    if a.shape[1] != b.shape[0]:
+        raise ValueError(f"Dimension mismatch: {a.shape[1]} vs {b.shape[0]}")
+    m, k = a.shape
+    n = b.shape[1]
+    if gemm == "blas":
+        return _f(np.matmul(a, b))
+    if gemm != "f2j":
+        raise ValueError(gemm)
+
+    def operand(x):
+        if x.flags.f_contiguous:
+            return "N", x, max(1, x.shape[0])
+        if x.flags.c_contiguous:          # Breeze `.t` view: data is the column-major array of x^T
+            return "T", x, max(1, x.shape[1])
+        xf = _f(x)                         # Breeze copies non-contiguous slices before calling BLAS
+        return "N", xf, max(1, xf.shape[0])
+
+    ta, abuf, lda = operand(a)
+    tb, bbuf, ldb = operand(b)
+    c = np.zeros((m, n), order="F")
+    dgemm_f2j(ta, tb, m, n, k, 1.0, abuf.reshape(-1, order="A"), 0, lda, bbuf.reshape(-1, order="A"), 0, ldb, 0.0,
+              c.reshape(-1, order="F"), 0, max(1, m))
+    return c
+
+
+def block_add(a: np.ndarray, b: np.ndarray) -> np.ndarray:
+    """SubMatrix.add (matrix/SubMatrix.scala:41-45): `this.denseBlock + other.denseBlock` (new matrix)."""
+    if a.shape != b.shape:
+        raise ValueError("matrix dimension mismatch")
+    return _f(a + b)
+
+
+def block_subtract(a: np.ndarray, b: np.ndarray) -> np.ndarray:
+    """matrix/SubMatrix.scala:60-64"""
+    if a.shape != b.shape:
+        raise ValueError("matrix dimension mismatch")
+    return _f(a - b)
+
+
+def block_transpose(a: np.ndarray) -> np.ndarray:
+    """`x._2.denseBlock.t.copy` (matrix/BlockMatrix.scala:517): materialised column-major transpose."""
+    a = _f(a)
+    out = np.empty((a.shape[1], a.shape[0]), order="F")
+    if a.size:
+        clib().mo_transpose_copy(a.shape[0], a.shape[1], _dp(a), max(1, a.shape[0]), _dp(out))
+    return out
+
+
+# --------------------------------------------------------------------------------------------
+# Integer host logic
+# --------------------------------------------------------------------------------------------
+def split_method(m: int, k: int, n: int, cores: int) -> Tuple[int, int, int]:
+    """MTUtils.splitMethod (utils/MTUtils.scala:150-175)."""
+    out = (C.c_int * 3)()
+    clib().mo_split_method(m, k, n, cores, out)
+    return out[0], out[1], out[2]
+
+
+def regrid_split_method(old_range: Sequence[Tuple[int, int]], new_sub_blk: int):
+    """MTUtils.splitMethod(oldRange, newSubBlk) (utils/MTUtils.scala:182-202)."""
+    status = []
+    for (start, end) in old_range:
+        start_id = start // new_sub_blk
+        end_id = end // new_sub_blk
+        num = end_id - start_id + 1
+        buf = []
+        tmp = 0
+        for j in range(num):
+            tmp_end = min((j + start_id + 1) * new_sub_blk - 1 - start, end - start)
+            buf.append((j + start_id, (tmp, tmp_end), ((tmp + start) % new_sub_blk, (tmp_end + start) % new_sub_blk)))
+            tmp = tmp_end + 1
+        status.append(buf)
+    return status
+
+
+def mult_seq(i: int, j: int, kk: int, m: int, k: int, n: int) -> int:
+    """seq of matrix/BlockMatrix.scala:163,168 = the partition of rdd/MatrixMultPartitioner.scala:12-22."""
+    return i * n * k + j * k + kk
+
+
+def hash_seed(seed: int) -> int:
+    return int(clib().mo_hash_seed(seed))
+
+
+def java_random_longs(seed: int, n: int) -> List[int]:
+    out = (C.c_int64 * n)()
+    clib().mo_java_random_longs(seed, n, out)
+    return [int(v) for v in out]
+
+
+def uniform_stream(partition_seed: int, first: int, n: int, lo: float = 0.0, hi: float = 1.0) -> np.ndarray:
+    """n successive UniformGenerator(lo,hi).nextValue() after setSeed(partition_seed), skipping `first`."""
+    out = np.empty(n)
+    if n:
+        clib().mo_uniform_fill(partition_seed, first, n, lo, hi, _dp(out))
+    return out
+
+
+def _ceil_div_d(total: int, parts: int) -> int:
+    return int(math.ceil(float(total) / float(parts)))
+
+
+# --------------------------------------------------------------------------------------------
+# Distributed matrices (L4): lists stand in for RDDs
+# --------------------------------------------------------------------------------------------
+class BlockMatrix:
+    """matrix/BlockMatrix.scala:28-67.  blocks: list of ((row, col), ndarray)."""
+
+    def __init__(self, blocks, n_rows: int = 0, n_cols: int = 0, blks_by_row: int = 0, blks_by_col: int = 0):
+        self.blocks = [((int(r), int(c)), _f(b)) for (r, c), b in blocks]
+        self._n_rows, self._n_cols, self._by_row, self._by_col = n_rows, n_cols, blks_by_row, blks_by_col
+
+    # :36-65 — lazily derived dims; `reduce` on an empty RDD throws (DistributedMatrixSuite "empty rows")
+    def num_rows(self) -> int:
+        if self._n_rows <= 0:
+            vals = [b.shape[0] for (r, c), b in self.blocks if c == 0]
+            if not vals:
+                raise RuntimeError("empty collection")
+            self._n_rows = sum(vals)
+        return self._n_rows
+
+    def num_cols(self) -> int:
+        if self._n_cols <= 0:
+            vals = [b.shape[1] for (r, c), b in self.blocks if r == 0]
+            if not vals:
+                raise RuntimeError("empty collection")
+            self._n_cols = sum(vals)
+        return self._n_cols
+
+    def num_blks_by_row(self) -> int:
+        if self._by_row <= 0:
+            self._by_row = sum(1 for (r, c), _ in self.blocks if c == 0)
+        return self._by_row
+
+    def num_blks_by_col(self) -> int:
+        if self._by_col <= 0:
+            self._by_col = sum(1 for (r, c), _ in self.blocks if r == 0)
+        return self._by_col
+
+    def to_breeze(self) -> np.ndarray:
+        """:70-85 — placement uses the ceil block size for every block."""
+        m, n = self.num_rows(), self.num_cols()
+        rl = _ceil_div_d(m, self.num_blks_by_row())
+        cl = _ceil_div_d(n, self.num_blks_by_col())
+        mat = np.zeros((m, n), order="F")
+        for (r, c), b in self.blocks:
+            mat[r * rl:r * rl + b.shape[0], c * cl:c * cl + b.shape[1]] = b
+        return mat
+
+    def multiply(self, other: "BlockMatrix", gemm: str = "f2j", reduce_order: str = "ascending") -> "BlockMatrix":
+        """:149-220.  Replicate A blocks n times / B blocks m times with seq keys, join inside the
+        m*k*n partitions, one dgemm per partition, reduceByKey over kk.  Spark fixes no order for the
+        k-way sum; `reduce_order` picks ascending / descending kk so tests can bound the spread."""
+        if self.num_cols() != other.num_rows():
+            raise ValueError(f"Dimension mismatch during matrix-matrix multiplication: {self.num_cols()} vs {other.num_rows()}")
+        if self.num_blks_by_col() == other.num_blks_by_row():
+            m, k, n = self.num_blks_by_row(), self.num_blks_by_col(), other.num_blks_by_col()
+            parts: Dict[int, dict] = {}
+            for (r, c), blk in self.blocks:          # :161-165
+                for j in range(n):
+                    parts.setdefault(r * n * k + j * k + c, {})["a"] = ((r, j), blk)
+            for (r, c), blk in other.blocks:         # :166-171
+                for i in range(m):
+                    parts.setdefault(i * n * k + c * k + r, {})["b"] = ((i, c), blk)
+            partial: Dict[Tuple[int, int], List[Tuple[int, np.ndarray]]] = {}
+            for seq in sorted(parts):                # join: partitions holding both sides
+                p = parts[seq]
+                if "a" in p and "b" in p:
+                    key = p["a"][0]
+                    partial.setdefault(key, []).append((seq, block_multiply(p["a"][1], p["b"][1], gemm)))
+            result = []
+            for key, lst in partial.items():          # :177 reduceByKey((a, b) => a.add(b))
+                lst.sort(key=lambda t: t[0], reverse=(reduce_order == "descending"))
+                acc = lst[0][1]
+                for _, blk in lst[1:]:
+                    acc = block_add(acc, blk)
+                result.append((key, acc))
+            return BlockMatrix(result, self.num_rows(), other.num_cols(), m, n)
+        if self.num_blks_by_col() % other.num_blks_by_row() == 0:      # :187-201
+            self._check_even_cols()
+            ratio = self.num_blks_by_col() // other.num_blks_by_row()
+            blks = []
+            for (r, c), mat in other.blocks:
+                for i in range(ratio):
+                    blks.append(((r * ratio + i, c), mat[i * mat.shape[0] // ratio:(i + 1) * mat.shape[0] // ratio, :]))
+            return self.multiply(BlockMatrix(blks), gemm, reduce_order)
+        if other.num_blks_by_row() % self.num_blks_by_col() == 0:      # :202-216 (slices rows of `this`, as written)
+            self._check_even_cols()
+            ratio = other.num_blks_by_row() // self.num_blks_by_col()
+            blks = []
+            for (r, c), mat in self.blocks:
+                for i in range(ratio):
+                    blks.append(((r * ratio + i, c), mat[i * mat.shape[0] // ratio:(i + 1) * mat.shape[0] // ratio, :]))
+            return BlockMatrix(blks).multiply(other, gemm, reduce_order)
+        raise ValueError("currently not supported for the two dimension of matrices")
+
+    def _check_even_cols(self):
+        if self.num_cols() % self.num_blks_by_col() != 0:
+            raise ValueError("only supported BlockMatrix which all the sub-matrices have the same cols")
+        if (self.num_cols() // self.num_blks_by_col()) % 2 != 0:
+            raise ValueError("only supported sub-matrices with even number cols")
+
+    def multiply_split(self, other, split_mode: Tuple[int, int, int], gemm: str = "f2j") -> "BlockMatrix":
+        """:131-147"""
+        if self.num_cols() != other.num_rows():
+            raise ValueError("Dimension mismatch during matrix-matrix multiplication")
+        m, k, n = split_mode
+        return self.to_block_matrix(m, k).multiply(other.to_block_matrix(k, n), gemm)
+
+    def multiply_local(self, B: np.ndarray, gemm: str = "f2j") -> "BlockMatrix":
+        """multiply(B: BDM) :280-303 — broadcast B; reduce over column blocks when there are several."""
+        if self.num_cols() != B.shape[0]:
+            raise ValueError(f"Dimension mismatch during matrix-matrix multiplication: {self.num_cols()} vs {B.shape[0]}")
+        B = _f(B)
+        if self.num_blks_by_col() == 1:
+            res = [((r, c), block_multiply(blk, B, gemm)) for (r, c), blk in self.blocks]
+            return BlockMatrix(res, self.num_rows(), B.shape[1], self.num_blks_by_row(), self.num_blks_by_col())
+        col_blk = _ceil_div_d(self.num_cols(), self.num_blks_by_col())
+        acc: Dict[Tuple[int, int], np.ndarray] = {}
+        for (r, c), blk in sorted(self.blocks, key=lambda t: t[0]):
+            start = c * col_blk
+            end = self.num_cols() if (c + 1) * col_blk > self.num_cols() else (c + 1) * col_blk
+            p = block_multiply(blk, B[start:end, :], gemm)
+            acc[(r, 0)] = block_add(acc[(r, 0)], p) if (r, 0) in acc else p
+        # the reference reports numBlksByCol() here although all keys have column 0 (:301)
+        return BlockMatrix(list(acc.items()), self.num_rows(), B.shape[1], self.num_blks_by_row(), self.num_blks_by_col())
+
+    def multiply_auto(self, other, cores: int, broadcast_threshold: int = 300, gemm: str = "f2j"):
+        """multiply(other, cores, broadcastThreshold) :87-122"""
+        if self.num_cols() != other.num_rows():
+            raise ValueError(f"Dimension mismatch during matrix-matrix multiplication: {self.num_cols()} vs {other.num_rows()}")
+        bsize = _jvm_int(broadcast_threshold * 1024 * 1024) // 8
+        if other.num_rows() * other.num_cols() <= bsize:
+            return self.multiply_local(other.to_breeze(), gemm)
+        if self.num_rows() * self.num_cols() <= bsize:
+            if isinstance(other, DenseVecMatrix):
+                return other.multiply_local(self.to_breeze(), gemm)       # :97-98 (operand-order quirk, kept)
+            raise NotImplementedError("multiplyBy (BlockMatrix.scala:309-335) is outside the hot-path table")
+        if isinstance(other, DenseVecMatrix) and _squareish(self.num_rows(), self.num_cols(), other.num_cols()):
+            s = int(math.floor(math.pow(3 * cores, 1.0 / 3.0)))
+            return self.multiply_split(other, (s, s, s), gemm)
+        return self.multiply_split(other, split_method(self.num_rows(), self.num_cols(), other.num_cols(), cores), gemm)
+
+    def scalar(self, op: str, b: float) -> "BlockMatrix":
+        """add(b) :368-371, subtract(b) :404-407, multiply(b) :229-232, divide(b) :432-435,
+        subtractBy :414-424, divideBy :442-452."""
+        f = {"add": lambda x: x + b, "subtract": lambda x: x - b, "multiply": lambda x: x * b, "divide": lambda x: x / b,
+             "subtractBy": lambda x: b - x, "divideBy": lambda x: b / x}[op]
+        return BlockMatrix([(k, _f(f(v))) for k, v in self.blocks], self.num_rows(), self.num_cols(),
+                           self.num_blks_by_row(), self.num_blks_by_col())
+
+    def add(self, other, subtract: bool = False):
+        """add :344-360 / subtract :380-396"""
+        if self.num_rows() != other.num_rows() or self.num_cols() != other.num_cols():
+            raise ValueError("matrix dimension mismatch")
+        op = block_subtract if subtract else block_add
+        if isinstance(other, DenseVecMatrix):
+            return self.to_dense_vec_matrix().add(other, subtract)
+        if self.num_blks_by_row() != other.num_blks_by_row() or self.num_blks_by_col() != other.num_blks_by_col():
+            return self.to_dense_vec_matrix().add(other.to_dense_vec_matrix(), subtract)
+        mine = dict(self.blocks)
+        res = [(key, op(mine[key], blk)) for key, blk in other.blocks if key in mine]      # join
+        return BlockMatrix(res, self.num_rows(), self.num_cols(), self.num_blks_by_row(), self.num_blks_by_col())
+
+    def dot_product(self, other):
+        """:486-507 (element-wise product; same-grid branch)"""
+        if self.num_rows() != other.num_rows() or self.num_cols() != other.num_cols():
+            raise ValueError("dimension mismatch")
+        if isinstance(other, DenseVecMatrix):
+            return self.to_dense_vec_matrix().dot_product(other)
+        mine = dict(self.blocks)
+        res = [(key, _f(mine[key] * blk)) for key, blk in other.blocks if key in mine]
+        return BlockMatrix(res, self.num_rows(), self.num_cols(), self.num_blks_by_row(), self.num_blks_by_col())
+
+    def sum(self) -> float:
+        """:467-472 — per block `data.sum` (sequential left fold), then reduce(_ + _)."""
+        total = None
+        for _, blk in self.blocks:
+            s = 0.0
+            for v in blk.reshape(-1, order="F"):
+                s += float(v)
+            total = s if total is None else total + s
+        if total is None:
+            raise RuntimeError("empty collection")
+        return total
+
+    def transpose(self) -> "BlockMatrix":
+        """:514-523"""
+        res = [((c, r), block_transpose(blk)) for (r, c), blk in self.blocks]
+        return BlockMatrix(res, self.num_cols(), self.num_rows(), self.num_blks_by_col(), self.num_blks_by_row())
+
+    def to_dense_vec_matrix(self) -> "DenseVecMatrix":
+        """:575-594"""
+        rl = _ceil_div_d(self.num_rows(), self.num_blks_by_row())
+        cl = _ceil_div_d(self.num_cols(), self.num_blks_by_col())
+        rows: Dict[int, np.ndarray] = {}
+        for (r, c), blk in self.blocks:
+            for i in range(blk.shape[0]):
+                vec = rows.setdefault(r * rl + i, np.zeros(self.num_cols()))
+                vec[cl * c:cl * c + blk.shape[1]] = blk[i, :]
+        return DenseVecMatrix(list(rows.items()))
+
+    def to_block_matrix(self, new_by_row: int, new_by_col: int) -> "BlockMatrix":
+        """:610-665 — re-grid via MTUtils.splitMethod(ranges, newLen)."""
+        if self._by_row == new_by_row and self._by_col == new_by_col:
+            return self
+        nr, nc = self.num_rows(), self.num_cols()
+        rl, cl = _ceil_div_d(nr, self.num_blks_by_row()), _ceil_div_d(nc, self.num_blks_by_col())
+        nrl, ncl = _ceil_div_d(nr, new_by_row), _ceil_div_d(nc, new_by_col)
+        new_br, new_bc = int(math.ceil(nr / nrl)), int(math.ceil(nc / ncl))
+        split_col = [(cl * i, min(cl * (i + 1) - 1, nc - 1)) for i in range(self.num_blks_by_col())]
+        split_row = [(rl * i, min(rl * (i + 1) - 1, nr - 1)) for i in range(self.num_blks_by_row())]
+        st_col = regrid_split_method(split_col, ncl)
+        st_row = regrid_split_method(split_row, nrl)
+        pieces: Dict[Tuple[int, int], list] = {}
+        for (r, c), blk in self.blocks:
+            for (rid, (or1, or2), (nr1, nr2)) in st_row[r]:
+                for (cid, (oc1, oc2), (nc1, nc2)) in st_col[c]:
+                    pieces.setdefault((rid, cid), []).append((nr1, nr2, nc1, nc2, blk[or1:or2 + 1, oc1:oc2 + 1].copy()))
+        res = []
+        for (rid, cid), lst in pieces.items():
+            row_len = nr - rid * nrl if (rid + 1) * nrl > nr else nrl
+            col_len = nc - cid * ncl if (cid + 1) * ncl > nc else ncl
+            mat = np.zeros((row_len, col_len), order="F")
+            for (r1, r2, c1, c2, piece) in lst:
+                mat[r1:r2 + 1, c1:c2 + 1] = piece
+            res.append(((rid, cid), mat))
+        return BlockMatrix(res, nr, nc, new_br, new_bc)
+
+    def save_block_lines(self) -> List[str]:
+        """saveToFileSystem(path, "blockmatrix") :550-555: `row-col-rows-cols:v,v,...` column-major."""
+        return [f"{r}-{c}-{b.shape[0]}-{b.shape[1]}:" + ",".join(_jdouble(v) for v in b.reshape(-1, order="F"))
+                for (r, c), b in self.blocks]
+
+
+class DenseVecMatrix:
+    """matrix/DenseVecMatrix.scala:41-69.  rows: list of (index, 1-D ndarray), any order."""
+
+    def __init__(self, rows, n_rows: int = 0, n_cols: int = 0):
+        self.rows = [(int(i), np.asarray(v, dtype=np.float64)) for i, v in rows]
+        self._n_rows, self._n_cols = n_rows, n_cols
+
+    def num_cols(self) -> int:
+        if self._n_cols <= 0:
+            if not self.rows:
+                raise RuntimeError("empty collection")
+            self._n_cols = self.rows[0][1].size
+        return self._n_cols
+
+    def num_rows(self) -> int:
+        if self._n_rows <= 0:
+            if not self.rows:
+                raise RuntimeError("empty collection")
+            self._n_rows = max(i for i, _ in self.rows) + 1
+        return self._n_rows
+
+    def to_breeze(self) -> np.ndarray:
+        """:74-84"""
+        mat = np.zeros((self.num_rows(), self.num_cols()), order="F")
+        for i, v in self.rows:
+            mat[i, :] = v
+        return mat
+
+    def to_block_matrix(self, num_by_row: int, num_by_col: int) -> BlockMatrix:
+        """:1259-1328"""
+        m_rows, m_cols = self.num_rows(), self.num_cols()
+        brs, bcs = _ceil_div_d(m_rows, num_by_row), _ceil_div_d(m_cols, num_by_col)
+        by_row, by_col = int(math.ceil(m_rows / brs)), int(math.ceil(m_cols / bcs))
+        groups: Dict[Tuple[int, int], list] = {}
+        for idx, vec in self.rows:
+            for i in range(by_col):
+                start = i * bcs
+                end = min(start + bcs, m_cols)
+                groups.setdefault((idx // brs, i), []).append((idx, vec[start:end].copy()))
+        res = []
+        for (br, bc), lst in groups.items():
+            row_base, col_base = br * brs, bc * bcs
+            sm_rows = m_rows - row_base if row_base + brs - 1 >= m_rows else brs
+            sm_cols = m_cols - col_base if col_base + bcs - 1 >= m_cols else bcs
+            mat = np.zeros((sm_rows, sm_cols), order="F")
+            for idx, v in lst:
+                mat[idx - row_base, :] = v
+            res.append(((br, bc), mat))
+        return BlockMatrix(res, m_rows, m_cols, by_row, by_col)
+
+    def to_blocks(self, m: int, k: int, n: int, mode: str):
+        """:1084-1223 — row->block conversion fused with the seq replication.
+        Returns list of ((row, col, seq), ndarray)."""
+        mode = mode.lower()
+        if mode not in ("right", "left"):
+            raise ValueError(f"only 'right' mode or 'left' mode is supported, you should change mode {mode}")
+        if not (m > 0 and k > 0 and n > 0):
+            raise ValueError(f"not supported (m, k, n): ({m}, {k}, {n})")
+        m_rows, m_cols = self.num_rows(), self.num_cols()
+        if mode == "right":
+            blkmat = self.to_block_matrix(m, k)
+            out = []
+            for (r, c), mat in blkmat.blocks:
+                for i in range(n):
+                    out.append(((r, i, r * n * k + i * k + c), mat))      # :1115,:1151
+            return out
+        blkmat = self.to_block_matrix(k, n)
+        out = []
+        for (r, c), mat in blkmat.blocks:
+            for i in range(m):
+                out.append(((i, c, i * n * k + c * k + r), mat))          # :1182,:1217
+        return out
+
+    def multiply_split(self, other, split_mode: Tuple[int, int, int], gemm: str = "f2j",
+                       reduce_order: str = "ascending") -> BlockMatrix:
+        """multiply(other, splitMode) :109-141"""
+        if self.num_cols() != other.num_rows():
+            raise ValueError(f"Dimension mismatch during matrix-matrix multiplication: {self.num_cols()} vs {other.num_rows()}")
+        m, k, n = split_mode
+        if isinstance(other, BlockMatrix):
+            # :136-139 re-grids `that` with (m, k) — the reference's quirk, reproduced
+            return self.to_block_matrix(m, k).multiply(other.to_block_matrix(m, k), gemm, reduce_order)
+        left = {key[2]: (key, mat) for key, mat in self.to_blocks(m, k, n, "right")}
+        right = {key[2]: (key, mat) for key, mat in other.to_blocks(m, k, n, "left")}
+        partial: Dict[Tuple[int, int], list] = {}
+        for seq in sorted(left):
+            if seq in right:
+                key = left[seq][0]
+                partial.setdefault((key[0], key[1]), []).append((seq, block_multiply(left[seq][1], right[seq][1], gemm)))
+        res = []
+        for key, lst in partial.items():
+            lst.sort(key=lambda t: t[0], reverse=(reduce_order == "descending"))
+            acc = lst[0][1]
+            for _, blk in lst[1:]:
+                acc = block_add(acc, blk)
+            res.append((key, acc))
+        return BlockMatrix(res, self.num_rows(), other.num_cols(), m, n)
+
+    def multiply_local(self, B: np.ndarray, gemm: str = "f2j", partitions: int = 2) -> "DenseVecMatrix":
+        """multiply(B: BDM) :1660-1680 — per partition: rowsMat(::, i) := row_i (K x rowsInPart),
+        matrix = B^T.copy * rowsMat, emit column i as row i."""
+        if self.num_cols() != B.shape[0]:
+            raise ValueError(f"Dimension mismatch during matrix-matrix multiplication: {self.num_cols()} vs {B.shape[0]}")
+        bt = _f(np.asarray(B, dtype=np.float64).T)         # B.t.copy
+        out = []
+        chunks = _partition(self.rows, partitions)
+        for part in chunks:
+            if not part:
+                continue
+            rows_mat = np.zeros((self.num_cols(), len(part)), order="F")
+            for i, (_, v) in enumerate(part):
+                rows_mat[:, i] = v
+            res = block_multiply(bt, rows_mat, gemm)
+            for i, (idx, _) in enumerate(part):
+                out.append((idx, res[:, i].copy()))
+        return DenseVecMatrix(out, 0, B.shape[1])
+
+    def multiply_auto(self, other, cores: int, broadcast_threshold: int = 300, gemm: str = "f2j"):
+        """multiply(other, cores, broadcastThreshold) :196-231"""
+        if self.num_cols() != other.num_rows():
+            raise ValueError(f"Dimension mismatch during matrix-matrix multiplication: {self.num_cols()} vs {other.num_rows()}")
+        bsize = _jvm_int(broadcast_threshold * 1024 * 1024) // 8
+        if other.num_rows() * other.num_cols() <= bsize:
+            return self.multiply_local(other.to_breeze(), gemm)
+        if self.num_rows() * self.num_cols() <= bsize:
+            if isinstance(other, DenseVecMatrix):
+                return other.multiply_local(self.to_breeze(), gemm)       # :206-207 (operand-order quirk, kept)
+            raise NotImplementedError("multiplyBy (BlockMatrix.scala:309-335) is outside the hot-path table")
+        if isinstance(other, DenseVecMatrix) and _squareish(self.num_rows(), self.num_cols(), other.num_cols()):
+            s = int(math.floor(math.pow(3 * cores, 1.0 / 3.0)))
+            return self.multiply_split(other, (s, s, s), gemm)
+        return self.multiply_split(other, split_method(self.num_rows(), self.num_cols(), other.num_cols(), cores), gemm)
+
+    def add(self, other, subtract: bool = False) -> "DenseVecMatrix":
+        """add :771-788 / subtract :795-810 — rows.join(that.rows), v1 + v2"""
+        if isinstance(other, BlockMatrix):
+            other = other.to_dense_vec_matrix()
+        if self.num_rows() != other.num_rows() or self.num_cols() != other.num_cols():
+            raise ValueError("Dimension mismatch")
+        theirs = dict(other.rows)
+        res = [(i, (v - theirs[i]) if subtract else (v + theirs[i])) for i, v in self.rows if i in theirs]
+        return DenseVecMatrix(res, self.num_rows(), self.num_cols())
+
+    def scalar(self, op: str, b: float) -> "DenseVecMatrix":
+        """:817-871"""
+        f = {"add": lambda x: x + b, "subtract": lambda x: x - b, "multiply": lambda x: x * b, "divide": lambda x: x / b,
+             "subtractBy": lambda x: b - x, "divideBy": lambda x: b / x}[op]
+        return DenseVecMatrix([(i, f(v)) for i, v in self.rows], self.num_rows(), self.num_cols())
+
+    def dot_product(self, other) -> "DenseVecMatrix":
+        if isinstance(other, BlockMatrix):
+            other = other.to_dense_vec_matrix()
+        theirs = dict(other.rows)
+        return DenseVecMatrix([(i, v * theirs[i]) for i, v in self.rows if i in theirs], self.num_rows(), self.num_cols())
+
+    def sum(self) -> float:
+        total = None
+        for _, v in self.rows:
+            s = 0.0
+            for x in v:
+                s += float(x)
+            total = s if total is None else total + s
+        if total is None:
+            raise RuntimeError("empty collection")
+        return total
+
+    def transpose(self, num_blocks: int = 2) -> BlockMatrix:
+        """:1420-1436 — toBlockMatrix(min(parallelism, rows/2), 1).transpose(); local[2] => 2"""
+        return self.to_block_matrix(min(num_blocks, self.num_rows() // 2), 1).transpose()
+
+    def save_lines(self) -> List[str]:
+        """saveToFileSystem :1042-1046: `index:v,v,...`"""
+        return [f"{i}:" + ",".join(_jdouble(x) for x in v) for i, v in self.rows]
+
+
+def _partition(seq: list, parts: int) -> List[list]:
+    """sc.parallelize(seq, parts) slicing (Spark ParallelCollectionRDD.slice positions)."""
+    n = len(seq)
+    return [seq[(i * n) // parts:((i + 1) * n) // parts] for i in range(parts)]
+
+
+def _jvm_int(v: int) -> int:
+    v &= 0xFFFFFFFF
+    return v - (1 << 32) if v & 0x80000000 else v
+
+
+def _squareish(m: int, k: int, n: int) -> bool:
+    """matrix/DenseVecMatrix.scala:208-211 (numRows()/numCols() is Long division)"""
+    ratio = float(m * n) / float(k * k)
+    q = m // k
+    return 0.8 < ratio < 1.2 and q < 1.2 and q > 0.8
+
+
+def _jdouble(v: float) -> str:
+    """java.lang.Double.toString for the values the tests use (shortest repr, always with a decimal point)."""
+    s = repr(float(v))
+    if "e" in s or "E" in s:
+        mant, exp = s.lower().split("e")
+        if "." not in mant:
+            mant += ".0"
+        return f"{mant}E{int(exp)}"
+    return s
+
+
+# --------------------------------------------------------------------------------------------
+# Loaders / generators (L3)
+# --------------------------------------------------------------------------------------------
+_SEP = re.compile(r",\s?|\s+")
+
+
+def load_matrix_file(path: str) -> DenseVecMatrix:
+    """MTUtils.loadMatrixFile (utils/MTUtils.scala:286-300): `rowIndex:v,v,...`, separators `,\\s?|\\s+`."""
+    rows = []
+    with open(path) as fh:
+        for line in fh:
+            line = line.rstrip("\n")
+            if not line:
+                continue
+            head, body = line.split(":")
+            rows.append((int(head), np.array([float(t) for t in _SEP.split(body) if t != ""])))
+    return DenseVecMatrix(rows)
+
+
+def load_block_matrix_lines(lines: Iterable[str]) -> BlockMatrix:
+    """MTUtils.loadBlockMatrixFile (utils/MTUtils.scala:324-340): `r-c-rows-cols:colmajor,...`"""
+    blocks = []
+    for line in lines:
+        line = line.strip()
+        if not line:
+            continue
+        head, body = line.split(":")
+        r, c, nr, nc = (int(t) for t in head.split("-"))
+        arr = np.array([float(t) for t in _SEP.split(body) if t != ""])
+        blocks.append(((r, c), arr.reshape((nr, nc), order="F")))
+    return BlockMatrix(blocks)
+
+
+def random_den_vec_matrix(n_rows: int, n_cols: int, num_partitions: int, seed: int, lo: float = 0.0,
+                          hi: float = 1.0) -> DenseVecMatrix:
+    """MTUtils.randomDenVecMatrix (utils/MTUtils.scala:63-73) -> RandomDenVecRDD (rdd/RandomRDD.scala:161-182):
+    partition p holds rows [p*N/P, (p+1)*N/P) (:38-41), seeded with the p-th nextLong of Random(seed);
+    each row is Array.fill(cols)(nextValue()) (:70-79)."""
+    seeds = java_random_longs(seed, num_partitions)
+    rows = []
+    start = 0
+    for p in range(num_partitions):
+        end = ((p + 1) * n_rows) // num_partitions
+        cnt = end - start
+        vals = uniform_stream(seeds[p], 0, cnt * n_cols, lo, hi).reshape(cnt, n_cols)
+        rows.extend((start + i, vals[i]) for i in range(cnt))
+        start = end
+    return DenseVecMatrix(rows, n_rows, n_cols)
+
+
+def random_block_matrix(n_rows: int, n_cols: int, num_by_row: int, num_by_col: int, seed: int, lo: float = 0.0,
+                        hi: float = 1.0) -> BlockMatrix:
+    """MTUtils.randomBlockMatrix (utils/MTUtils.scala:34-50) -> RandomBlockRDD (rdd/RandomRDD.scala:184-223):
+    one partition per block in row-major BlockID order, BDM.create(rows, cols, Array.fill(..)) column-major."""
+    brs, bcs = _ceil_div_d(n_rows, num_by_row), _ceil_div_d(n_cols, num_by_col)
+    by_row, by_col = int(math.ceil(n_rows / brs)), int(math.ceil(n_cols / bcs))
+    seeds = java_random_longs(seed, by_row * by_col)
+    blocks = []
+    for idx in range(by_row * by_col):
+        i, j = divmod(idx, by_col)
+        rows = brs
+        if idx >= (by_row - 1) * by_col and brs * by_row > n_rows:
+            rows = n_rows - brs * (by_row - 1)
+        cols = bcs
+        if (idx + 1) % by_col == 0 and bcs * by_col > n_cols:
+            cols = n_cols - bcs * (by_col - 1)
+        vals = uniform_stream(seeds[idx], 0, rows * cols, lo, hi)
+        blocks.append(((i, j), vals.reshape((rows, cols), order="F")))
+    return BlockMatrix(blocks, n_rows, n_cols, by_row, by_col)
