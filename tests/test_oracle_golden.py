@@ -1,0 +1,196 @@
+"""Pins the CPU oracle against the reference's own golden vectors (DistributedMatrixSuite.scala) — CPU only."""
+import hashlib
+
+import numpy as np
+import pytest
+
+from tests import marlin_cases as mc
+
+
+def _dvm(rm):
+    return rm.DenseVecMatrix([(i, np.array(v)) for i, v in mc.DATA_ROWS])
+
+
+def _blk(rm):
+    return rm.BlockMatrix([(k, np.array(v)) for k, v in mc.BLKS])
+
+
+def _blocks_equal(bm, expected):
+    got = {k: v for k, v in bm.blocks}
+    assert set(got) == set(expected)
+    for k, v in expected.items():
+        assert np.array_equal(got[k], np.array(v)), (k, got[k])
+
+
+@pytest.mark.parametrize("gemm", ["f2j", "blas"])
+class TestReferenceSuite:
+    def test_matrix_size(self, oracle, gemm):            # DMS.scala:42-51
+        mat, ma = _dvm(oracle), _blk(oracle)
+        assert (mat.num_rows(), mat.num_cols()) == (4, 4)
+        assert (ma.num_rows(), ma.num_cols(), ma.num_blks_by_row(), ma.num_blks_by_col()) == (4, 4, 2, 2)
+
+    def test_empty_rows(self, oracle, gemm):             # :53-71
+        with pytest.raises(RuntimeError):
+            oracle.DenseVecMatrix([]).num_rows()
+        with pytest.raises(RuntimeError):
+            oracle.DenseVecMatrix([]).num_cols()
+        with pytest.raises(RuntimeError):
+            oracle.BlockMatrix([]).num_rows()
+        with pytest.raises(RuntimeError):
+            oracle.BlockMatrix([]).num_cols()
+
+    def test_to_breeze(self, oracle, gemm):              # :73-84
+        assert np.array_equal(_dvm(oracle).to_breeze(), mc.EXPECTED_DENSE)
+        assert np.array_equal(_blk(oracle).to_breeze(), mc.EXPECTED_DENSE)
+
+    def test_to_block_matrix(self, oracle, gemm):        # :86-105
+        mat = _dvm(oracle)
+        blk = mat.to_block_matrix(2, 2)
+        _blocks_equal(blk, dict(mc.BLKS))
+        assert np.array_equal(mat.to_block_matrix(1, 4).to_breeze(), mc.EXPECTED_DENSE)
+
+    def test_to_dense_vec_matrix(self, oracle, gemm):    # :108-119
+        rows = dict(_blk(oracle).to_dense_vec_matrix().rows)
+        for i in range(4):
+            assert np.array_equal(rows[i], mc.EXPECTED_DENSE[i])
+
+    def test_elementwise(self, oracle, gemm):            # :164-205
+        mat, ma = _dvm(oracle), _blk(oracle)
+        for x in (mat, ma):
+            assert np.array_equal(x.scalar("add", 1).to_breeze(), mc.ELE_ADD1)
+            assert np.array_equal(x.add(x).to_breeze(), mc.ADD_SELF)
+            assert np.array_equal(x.scalar("subtract", 1).to_breeze(), mc.ELE_SUB1)
+            assert np.array_equal(x.add(x, subtract=True).to_breeze(), np.zeros((4, 4)))
+            assert np.array_equal(x.scalar("multiply", 2).to_breeze(), mc.ADD_SELF)
+            assert np.array_equal(x.scalar("divide", 2).to_breeze(), mc.DIVIDE2)
+        assert np.array_equal(ma.add(mat).to_breeze(), mc.ADD_SELF)
+        assert np.array_equal(ma.add(mat, subtract=True).to_breeze(), np.zeros((4, 4)))
+
+    def test_multiply_broadcast_choice(self, oracle, gemm):     # :225-234
+        mat = _dvm(oracle)
+        assert np.array_equal(mat.multiply_auto(mat, 2, gemm=gemm).to_breeze(), mc.EXPECTED_PRODUCT)
+
+    @pytest.mark.parametrize("split", [(2, 2, 1), (2, 1, 2), (2, 2, 2)])
+    def test_new_matrix_multiplication(self, oracle, gemm, split):   # :236-249
+        mat = _dvm(oracle)
+        assert np.array_equal(mat.multiply_split(mat, split, gemm=gemm).to_breeze(), mc.EXPECTED_PRODUCT)
+
+    def test_multiply_local_matrix(self, oracle, gemm):         # :251-267
+        assert np.array_equal(_dvm(oracle).multiply_local(mc.EXPECTED_DENSE, gemm=gemm).to_breeze(), mc.EXPECTED_PRODUCT)
+
+    def test_multiply_block_matrix(self, oracle, gemm):         # :269-287
+        mat, ma = _dvm(oracle), _blk(oracle)
+        assert np.array_equal(mat.multiply_auto(ma, 2, gemm=gemm).to_breeze(), mc.EXPECTED_PRODUCT)
+        _blocks_equal(ma.multiply(ma, gemm=gemm), mc.EXPECTED_PRODUCT_BLOCKS)
+
+    def test_block_times_densevec_broadcast(self, oracle, gemm):   # :289-299
+        assert np.array_equal(_blk(oracle).multiply_auto(_dvm(oracle), 2, gemm=gemm).to_breeze(), mc.EXPECTED_PRODUCT)
+
+    def test_transpose(self, oracle, gemm):                     # :302-316
+        _blocks_equal(_dvm(oracle).transpose(), mc.EXPECTED_T_DVM_BLOCKS)
+        _blocks_equal(_blk(oracle).transpose(), mc.EXPECTED_T_BLK_BLOCKS)
+
+    def test_sum(self, oracle, gemm):                           # :319-324
+        assert _dvm(oracle).sum() == mc.SUM
+        assert _blk(oracle).sum() == mc.SUM
+
+    def test_dot_product(self, oracle, gemm):                   # :326-338
+        mat, ma = _dvm(oracle), _blk(oracle)
+        for a, b in ((mat, mat), (mat, ma), (ma, mat), (ma, ma)):
+            assert np.array_equal(a.dot_product(b).to_breeze(), mc.DOT_PRODUCT)
+
+    def test_block_to_block(self, oracle, gemm):                # :411-418
+        blk1 = _dvm(oracle).to_block_matrix(2, 2)
+        assert np.array_equal(blk1.to_block_matrix(1, 4).to_breeze(), blk1.to_breeze())
+        assert np.array_equal(blk1.to_block_matrix(4, 1).to_breeze(), blk1.to_breeze())
+
+    def test_block_multiply_block_regrid(self, oracle, gemm):   # :420-432
+        mat = _dvm(oracle)
+        m = mat.to_block_matrix(2, 2).to_block_matrix(2, 1)
+        assert np.array_equal(m.multiply(mat.to_block_matrix(1, 4), gemm=gemm).to_breeze(), mc.EXPECTED_PRODUCT)
+
+    def test_block_multiply_broadcast(self, oracle, gemm):      # :434-448
+        assert np.array_equal(_blk(oracle).multiply_local(mc.EXPECTED_DENSE, gemm=gemm).to_breeze(), mc.EXPECTED_PRODUCT)
+
+
+def test_ratio_resplit_branches(oracle):
+    """BlockMatrix.scala:187-216 (untested by the reference suite): (2x4 grid) x (2x2 grid) and the mirror."""
+    rng = np.random.default_rng(5)
+    A = rng.integers(-3, 4, size=(8, 8)).astype(float)
+    B = rng.integers(-3, 4, size=(8, 8)).astype(float)
+    a = oracle.DenseVecMatrix(list(enumerate(A))).to_block_matrix(2, 4)
+    b = oracle.DenseVecMatrix(list(enumerate(B))).to_block_matrix(2, 2)
+    assert np.array_equal(a.multiply(b).to_breeze(), A @ B)
+
+
+def test_split_method_and_seq(oracle):
+    # cfg3 -> (2,2,2); MTUtils.scala:150-175
+    assert oracle.split_method(16384, 16384, 16384, 8) == (2, 2, 2)
+    assert oracle.split_method(1048576, 1024, 1024, 8) == (8, 1, 1)
+    assert oracle.split_method(100, 100, 100, 1) == (1, 1, 1)
+    assert oracle.split_method(10, 1000, 10, 4) == (1, 4, 1)
+    assert oracle.mult_seq(1, 0, 1, 2, 2, 2) == 5     # i*n*k + j*k + kk
+
+
+def test_config1_files(oracle, golden_dir):
+    """BASELINE config[0]: data/a.100.100 x data/b.100.100 through loadMatrixFile -> multiply (broadcast branch and
+    the (2,2,2) shuffle path); known answers from SURVEY §8(c)."""
+    for name, sha in mc.SHA256.items():
+        assert hashlib.sha256((golden_dir / name).read_bytes()).hexdigest() == sha
+    a = oracle.load_matrix_file(str(golden_dir / "a.100.100"))
+    b = oracle.load_matrix_file(str(golden_dir / "b.100.100"))
+    assert (a.num_rows(), a.num_cols(), b.num_rows(), b.num_cols()) == (100, 100, 100, 100)
+    A, B = a.to_breeze(), b.to_breeze()
+    assert A.sum() == pytest.approx(mc.CFG1["sumA"], rel=1e-12)
+    assert B.sum() == pytest.approx(mc.CFG1["sumB"], rel=1e-12)
+    for gemm in ("f2j", "blas"):
+        c1 = a.multiply_auto(b, 2, gemm=gemm).to_breeze()
+        c2 = a.multiply_split(b, (2, 2, 2), gemm=gemm).to_breeze()
+        for c in (c1, c2):
+            assert c[0, 0] == pytest.approx(mc.CFG1["C00"], rel=1e-12)
+            assert c[0, 1] == pytest.approx(mc.CFG1["C01"], rel=1e-12)
+            assert c[99, 99] == pytest.approx(mc.CFG1["C9999"], rel=1e-12)
+            assert c.sum() == pytest.approx(mc.CFG1["sumC"], rel=1e-11)
+            assert np.trace(c) == pytest.approx(mc.CFG1["traceC"], rel=1e-11)
+            assert np.linalg.norm(c) == pytest.approx(mc.CFG1["frobC"], rel=1e-12)
+    assert (A + B).sum() == pytest.approx(mc.CFG1["sumAplusB"], rel=1e-12)
+
+
+def test_f2j_dgemm_matches_exact_rational(oracle):
+    """The F2J-order dgemm equals an exactly rounded dot product to within K ulp-level rounding (no FMA)."""
+    from fractions import Fraction
+    rng = np.random.default_rng(1)
+    A = np.asfortranarray(rng.random((7, 9)) - 0.5)
+    B = np.asfortranarray(rng.random((9, 5)) - 0.5)
+    C = oracle.block_multiply(A, B, "f2j")
+    for i in range(7):
+        for j in range(5):
+            exact = sum(Fraction(A[i, l]) * Fraction(B[l, j]) for l in range(9))
+            bound = sum(abs(Fraction(A[i, l]) * Fraction(B[l, j])) for l in range(9)) * Fraction(10, 2 ** 53)
+            assert abs(Fraction(C[i, j]) - exact) <= bound
+    # transposed views go through the 'T' branches of dgemm.f
+    assert np.allclose(oracle.block_multiply(np.ascontiguousarray(A), B, "f2j"), C, rtol=0, atol=1e-15)
+    assert np.allclose(oracle.block_multiply(A, np.ascontiguousarray(B), "f2j"), C, rtol=0, atol=1e-15)
+
+
+def test_rng_properties(oracle):
+    """XORShift / hashSeed / java.util.Random restatement: structural checks (the reference has no golden values
+    for its generators — parity unpinned)."""
+    # java.util.Random(42).nextLong() is a widely published constant of the JDK LCG
+    assert oracle.java_random_longs(42, 1)[0] == -5025562857975149833
+    v = oracle.uniform_stream(7, 0, 1000)
+    assert v.min() >= 0.0 and v.max() < 1.0 and 0.4 < v.mean() < 0.6
+    assert np.array_equal(oracle.uniform_stream(7, 10, 5), v[10:15])          # skip-ahead consistency
+    m = oracle.random_den_vec_matrix(10, 3, 2, seed=3)
+    assert m.to_breeze().shape == (10, 3) and [i for i, _ in m.rows] == list(range(10))
+    b = oracle.random_block_matrix(5, 7, 2, 3, seed=3)
+    assert b.to_breeze().shape == (5, 7)
+    assert sorted(k for k, _ in b.blocks) == [(i, j) for i in range(2) for j in range(3)]
+    assert [blk.shape for _, blk in sorted(b.blocks)] == [(3, 3), (3, 3), (3, 1), (2, 3), (2, 3), (2, 1)]
+
+
+def test_save_load_roundtrip(oracle):
+    blk = oracle.BlockMatrix([(k, np.array(v)) for k, v in mc.BLKS])
+    again = oracle.load_block_matrix_lines(blk.save_block_lines())
+    assert np.array_equal(again.to_breeze(), mc.EXPECTED_DENSE)
+    assert blk.save_block_lines()[0] == "0-0-2-2:0.0,2.0,1.0,3.0"
