@@ -1,0 +1,320 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the hot path: N x N dense fp64 multiply (BASELINE.json metric).
+
+Workload (BASELINE.json configs[2], the configuration the targets are quoted on, and it fits one GPU):
+16384 x 16384 fp64 BlockMatrix multiply on a 2x2 block grid, (m,k,n) = (2,2,2) => 8 block products of
+8192^3 (`BlockMatrix.multiply(other: BlockMatrix)`, matrix/BlockMatrix.scala:149-186), synthetic
+U[0,1) inputs from the on-device XORShift generator (MTUtils.randomBlockMatrix).  One step = one full
+multiply.  The same problem runs at N = 1, 2, 4, 8 GPUs ("strong" scaling); blocks are placed by
+MatrixElemOpPartitioner order mod N and tiles move with grouped NCCL send/recv.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--size S]          (N>1: launched by torchrun)
+  python bench.py --impl reference ...   CPU restatement of the reference path (oracle port) on host cores
+
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+FP64_PEAK_TFLOPS_MEASURED = 37.1   # scripts/dmma_bench.cu on this pool's B200 (profiles/r01_probe_*): 148 SM x 64 DFMA/clk x 1.965 GHz
+METRIC = "fp64 dense multiply throughput (2*N^3 flop), 16384x16384 BlockMatrix 2x2 grid"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--size", type=int, default=16384)
+    ap.add_argument("--grid", type=int, default=2)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------ CPU arm
+def cpu_port_sample(size: int, grid: int, target_seconds: float, steps: int = 1, warmup: int = 0):
+    """The reference algorithm on host cores (oracle port, numpy/OpenBLAS dgemm on all threads), on a BOUNDED
+    sample of the workload: one of the (grid^3) block products A(0,0) * B(0,0)[:, :w], w chosen so a step takes
+    about `target_seconds`.  Returns (tflops, cores, sample description, ms per step)."""
+    import numpy as np
+    from oracle import reference_model as rm
+    cores = os.cpu_count() or 1
+    os.environ.setdefault("OPENBLAS_NUM_THREADS", str(cores))
+    bs = size // grid
+    rng = np.random.default_rng(42)
+    probe = 1024
+    a = np.asfortranarray(rng.random((probe, probe)))
+    b = np.asfortranarray(rng.random((probe, probe)))
+    rm.block_multiply(a, b, "blas")
+    t0 = time.perf_counter()
+    rm.block_multiply(a, b, "blas")
+    gf = 2.0 * probe ** 3 / (time.perf_counter() - t0) / 1e9
+    w = int(target_seconds * gf * 1e9 / (2.0 * bs * bs))
+    w = max(64, min(bs, (w // 64) * 64))
+    A = np.asfortranarray(rng.random((bs, bs)))
+    B = np.asfortranarray(rng.random((bs, w)))
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        C = rm.block_multiply(A, B, "blas")          # SubMatrix.multiply -> dgemm (SubMatrix.scala:87-91)
+        if grid > 1:
+            C = rm.block_add(C, C)                    # one reduceByKey add per partial (BlockMatrix.scala:177)
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    sec = statistics.median(times)
+    flops = 2.0 * bs * bs * w
+    sample = (f"one block product A(0,0)[{bs}x{bs}] * B(0,0)[:, :{w}] + one partial add, numpy/OpenBLAS dgemm, "
+              f"{cores} threads; median of {len(times)}")
+    return flops / sec / 1e12, cores, sample, sec * 1e3
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    tf, cores, sample, ms = cpu_port_sample(args.size, args.grid, args.cpu_seconds, steps=max(1, args.steps),
+                                            warmup=min(1, args.warmup))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": tf, "unit": "TFLOP/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{args.size}x{args.size} fp64 BlockMatrix multiply, {args.grid}x{args.grid} grid (bounded sample per step)"},
+        "cpu_baseline": {"value": tf, "unit": "TFLOP/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": tf, "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "reference = CPU restatement (oracle port, OpenBLAS dgemm standing in for Breeze->netlib-java); the Scala/Spark "
+                "reference itself cannot run here (no JVM)",
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.12)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for l in self.lines:
+            f = [x.strip() for x in l.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        loaded = [s for s, p in zip(sm, pw) if p > 300] or sm
+        return {"sm_mhz": statistics.median(loaded) if loaded else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------ GPU arm
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import marlin_b200 as mb
+    from marlin_b200 import _native as nat, comm, profiling
+
+    ws = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if ws != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={ws}: launch with torchrun --nproc-per-node {args.gpus}")
+    torch.cuda.set_device(local_rank)
+    if ws > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    rt = mb.Runtime.get()
+    N, g = args.size, args.grid
+    flops = 2.0 * N * N * N
+
+    A = mb.MTUtils.randomBlockMatrix(None, N, N, g, g, seed=42)
+    B = mb.MTUtils.randomBlockMatrix(None, N, N, g, g, seed=43)
+    torch.cuda.synchronize()
+
+    def barrier():
+        if ws > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step():
+        return A.multiply(B)                       # BlockMatrix.multiply(other: BlockMatrix)
+
+    for _ in range(args.warmup):
+        Cm = step()
+        del Cm
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    profiling.enable(True)
+    l0 = rt.launch_count()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        Cm = step()
+        del Cm
+    e1.record()
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    phases = profiling.collect()
+    profiling.enable(False)
+    launches = rt.launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms_total], device="cuda", dtype=torch.float64)
+    if ws > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item()) / args.steps
+    value = flops / (ms_step * 1e-3) / 1e12
+
+    # dominant kernel: the per-block DMMA GEMM (8192^3 at the default size); average launch duration from the
+    # CUDA events bracketing each launch on the launching stream
+    bs = N // g
+    gemm_ms, gemm_n = phases.get("gemm", (0.0, 0))
+    gemm_avg_ms = gemm_ms / max(1, gemm_n)
+    achieved = 2.0 * bs ** 3 / (gemm_avg_ms * 1e-3) / 1e12 if gemm_n else None
+    traffic = None
+    summary = ROOT / "profiles" / "ncu_summary.json"
+    if summary.exists():
+        try:
+            traffic = json.loads(summary.read_text()).get("gemm_f64_dmma", {}).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {"bound": "tensor", "achieved": achieved, "peak": FP64_PEAK_TFLOPS_MEASURED, "unit": "TFLOP/s",
+                "frac": (achieved / FP64_PEAK_TFLOPS_MEASURED) if achieved else None, "traffic": traffic,
+                "kernel": "gemm_f64_dmma_kernel<N,N> (DMMA.8x8x4 + TMA)", "launch_ms_avg": gemm_avg_ms,
+                "flops_per_launch": 2.0 * bs ** 3,
+                "peak_source": "measured fp64 DMMA issue peak on this pool's B200 (scripts/dmma_bench.cu, "
+                               "profiles/r01_probe_dmma_peak_and_gemm_v1.log); MEASURED_PEAKS.json carries no fp64 entry; "
+                               "cuBLAS dgemm on the same GPU measured 36.2 TFLOP/s"}
+
+    # ---- e2e: host buffers -> H2D -> multiply -> D2H, through the public API, every step ----
+    e2e = None
+    if not args.no_e2e:
+        own_a = [(b, s) for b, s in A.blocks]
+        own_b = [(b, s) for b, s in B.blocks]
+        pin = lambda s: torch.empty(s.rows * s.cols, dtype=torch.float64).pin_memory().copy_(s.buf[: s.rows * s.cols].cpu())
+        host_a = [(b, pin(s), s.rows, s.cols) for b, s in own_a]
+        host_b = [(b, pin(s), s.rows, s.cols) for b, s in own_b]
+        host_c = {}
+        h2d = sum(t_.numel() * 8 for _, t_, _, _ in host_a + host_b)
+        d2h_box = [0]
+
+        def e2e_step():
+            da = [(b, mb.SubMatrix(buf=t_.to(rt.device, non_blocking=True), rows=r, cols=c)) for b, t_, r, c in host_a]
+            db = [(b, mb.SubMatrix(buf=t_.to(rt.device, non_blocking=True), rows=r, cols=c)) for b, t_, r, c in host_b]
+            Ad = mb.BlockMatrix(da, N, N, g, g)
+            Bd = mb.BlockMatrix(db, N, N, g, g)
+            Cd = Ad.multiply(Bd)
+            nbytes = 0
+            for b, s in Cd.blocks:
+                key = (b.row, b.column)
+                if key not in host_c:
+                    host_c[key] = torch.empty(s.rows * s.cols, dtype=torch.float64).pin_memory()
+                host_c[key].copy_(s.buf[: s.rows * s.cols], non_blocking=True)
+                nbytes += s.rows * s.cols * 8
+            d2h_box[0] = nbytes
+            torch.cuda.synchronize()
+
+        e2e_steps = max(2, min(args.steps, 3))
+        e2e_step()
+        barrier()
+        e0.record()
+        for _ in range(e2e_steps):
+            e2e_step()
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
+        bts = torch.tensor([float(h2d), float(d2h_box[0])], device="cuda", dtype=torch.float64)
+        if ws > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dist.all_reduce(bts, op=dist.ReduceOp.SUM)
+        e2e_ms = float(t.item()) / e2e_steps
+        e2e = {"value": flops / (e2e_ms * 1e-3) / 1e12, "unit": "TFLOP/s", "h2d_bytes_per_step": int(bts[0].item()),
+               "d2h_bytes_per_step": int(bts[1].item()), "ms_per_step": e2e_ms, "steps": e2e_steps,
+               "path": "pinned host blocks -> H2D -> BlockMatrix.multiply -> D2H of C blocks, every step"}
+
+    cpu_baseline = None
+    if rank == 0 and ws == 1 and not args.no_cpu_baseline:
+        tf, cores, sample, _ = cpu_port_sample(N, g, args.cpu_seconds)
+        cpu_baseline = {"value": tf, "unit": "TFLOP/s", "cores": cores, "kind": "port", "sample": sample}
+
+    if rank == 0:
+        par = {1: "1 GPU: all 8 block products local, k-sum accumulated in the GEMM epilogue",
+               2: "2 GPUs: 4 products each, k-sum local", 4: "4 GPUs: 2 products each (same C tile), k-sum local",
+               8: "8 GPUs: 1 product each (RDD partition == GPU), A/B tiles via grouped NCCL send/recv, pairwise reduce of partials"}
+        line = {
+            "metric": METRIC, "value": value, "unit": "TFLOP/s", "n_gpus": ws, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": f"{N}x{N} fp64 BlockMatrix multiply, {g}x{g} block grid, (m,k,n)=({g},{g},{g}) "
+                                   f"[BASELINE.json configs[2]; also the 1-GPU target size]",
+                       "parallelism": par.get(ws, f"{ws} GPUs"),
+                       "l2": "inputs (2 GiB per operand) are far larger than the 126 MB L2; no explicit flush",
+                       "inputs": "U[0,1) fp64 from the on-device XORShift generator (MTUtils.randomBlockMatrix, seeds 42/43)"},
+            "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu_baseline, "gpu_launches": int(launches),
+            "clocks": clocks,
+            "phases_ms_per_step": {k: v[0] / args.steps for k, v in phases.items()},
+            "pct_of_fp64_peak": 100.0 * value / (FP64_PEAK_TFLOPS_MEASURED * ws),
+        }
+        print(json.dumps(line), flush=True)
+    if ws > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -17,6 +17,7 @@ import torch
 
 from .. import _native as nat
 from .. import comm
+from .. import profiling
 from ..runtime import Runtime, world
 from .block import BlockID
 from .distributed_matrix import DistributedMatrix
@@ -221,7 +222,8 @@ class BlockMatrix(DistributedMatrix):
                 r, c = dims_a(*key[1:]) if key[0] == "A" else dims_b(*key[1:])
                 return torch.empty(r * c, dtype=dtype_a, device=dev)
 
-            got = comm.exchange(sends, send_bufs, alloc, rank)
+            with profiling.phase("exchange"):
+                got = comm.exchange(sends, send_bufs, alloc, rank)
             for key, buf in got.items():
                 r, c = dims_a(*key[1:]) if key[0] == "A" else dims_b(*key[1:])
                 (a_tiles if key[0] == "A" else b_tiles)[key[1:]] = SubMatrix(buf=buf, rows=r, cols=c, ld=max(1, r))
@@ -229,10 +231,11 @@ class BlockMatrix(DistributedMatrix):
         partial: Dict[Tuple[int, int], SubMatrix] = {}
         for (i, j, kk) in plan.products.get(rank, []):
             a, b = a_tiles[(i, kk)], b_tiles[(kk, j)]
-            if (i, j) in partial:
-                a.multiply(b, out=partial[(i, j)], accumulate=True)
-            else:
-                partial[(i, j)] = a.multiply(b)
+            with profiling.phase("gemm"):
+                if (i, j) in partial:
+                    a.multiply(b, out=partial[(i, j)], accumulate=True)
+                else:
+                    partial[(i, j)] = a.multiply(b)
         if ws > 1 and plan.c_reduces:
             # reduceByKey across ranks (:177): partials travel to the C tile's owner and are added there
             sends = [(s, d, ("C",) + key + (s,)) for s, d, key in plan.c_reduces]
@@ -243,10 +246,11 @@ class BlockMatrix(DistributedMatrix):
                 p = partial[key[1:3]]
                 return torch.empty(p.rows * p.cols, dtype=p.buf.dtype, device=p.buf.device)
 
-            got = comm.exchange(sends, send_bufs, alloc_c, rank)
-            for key, buf in sorted(got.items()):
-                p = partial[key[1:3]]
-                p.add_(SubMatrix(buf=buf, rows=p.rows, cols=p.cols, ld=max(1, p.rows)))
+            with profiling.phase("reduce"):
+                got = comm.exchange(sends, send_bufs, alloc_c, rank)
+                for key, buf in sorted(got.items()):
+                    p = partial[key[1:3]]
+                    p.add_(SubMatrix(buf=buf, rows=p.rows, cols=p.cols, ld=max(1, p.rows)))
             for s, d, key in plan.c_reduces:
                 if s == rank:
                     partial.pop(key, None)
