@@ -185,13 +185,13 @@ def run_ours(args):
     def step():
         return A.multiply(B)                       # BlockMatrix.multiply(other: BlockMatrix)
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()           # nvidia-smi needs ~1 s to start sampling: start before warm-up, read only loaded samples
     for _ in range(args.warmup):
         Cm = step()
         del Cm
     barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     profiling.enable(True)
     l0 = rt.launch_count()
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
