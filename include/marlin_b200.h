@@ -161,6 +161,17 @@ int32_t mb_block_len(int64_t total, int32_t parts, int32_t* block_len, int32_t* 
 int32_t mb_matmul_blocked(mb_ctx* ctx, mb_block* const* A_tiles, mb_block* const* B_tiles,
                           int32_t m, int32_t k, int32_t n, mb_block* const* C_tiles);
 
+/* The same multiply for JVM-held blocks (HOST column-major fp64 arrays in, host arrays out): the entry a
+ * `BlockMatrix.multiply` whose SubMatrix data still lives on the heap would bind.  A_host[i*k+kk] is the packed
+ * (row_len[i] x k_len[kk]) tile, B_host[kk*n+j] the (k_len[kk] x col_len[j]) tile, C_host[i*n+j] receives the
+ * (row_len[i] x col_len[j]) result.  Uploads, the m*k*n DMMA products (seq order, kk accumulated in the epilogue)
+ * and downloads are pipelined on separate streams: tiles are uploaded in first-use order and every C tile
+ * starts its D2H as soon as its last partial is done.  Pinned host memory gives full PCIe overlap; pageable
+ * memory still works (the copies just serialise).  This is the end-to-end path bench.py times at N=1. */
+int32_t mb_matmul_blocked_host(mb_ctx* ctx, const double* const* A_host, const double* const* B_host,
+                               int32_t m, int32_t k, int32_t n, const int32_t* row_len, const int32_t* k_len,
+                               const int32_t* col_len, double* const* C_host);
+
 /* ---- rows <-> blocks on device (matrix/DenseVecMatrix.scala:1084-1223, 1259-1328;
  *      matrix/BlockMatrix.scala:575-594): a DenseVecMatrix shard is a row-major (rows x cols)
  *      buffer, i.e. a transposed block; these are strided copies (mb_block_copy on views). */

@@ -73,6 +73,8 @@ SIGNATURES = {
     "mb_mult_partition": (c_i32, [c_i32, c_i32, c_i32, c_i32, c_i32, c_i32]),
     "mb_elem_partition": (c_i32, [c_i32, c_i32, c_i32]),
     "mb_block_len": (c_i32, [c_i64, c_i32, C.POINTER(c_i32), C.POINTER(c_i32)]),
+    "mb_matmul_blocked_host": (c_i32, [c_ctx, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), c_i32, c_i32, c_i32,
+                                       C.POINTER(c_i32), C.POINTER(c_i32), C.POINTER(c_i32), C.POINTER(C.c_void_p)]),
     "mb_matmul_blocked": (c_i32, [c_ctx, C.POINTER(c_blk), C.POINTER(c_blk), c_i32, c_i32, c_i32, C.POINTER(c_blk)]),
 }
 

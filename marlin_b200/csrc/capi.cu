@@ -12,6 +12,7 @@
 #include <cstring>
 #include <new>
 #include <atomic>
+#include <vector>
 
 struct mb_ctx {
     int device = 0;
@@ -22,6 +23,10 @@ struct mb_ctx {
     double* scratch = nullptr;          // sum partials + result
     double* host_scalar = nullptr;      // pinned
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // pipelined host<->device path (mb_matmul_blocked_host): copy streams + a grow-only device workspace
+    cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
+    void* workspace = nullptr;
+    size_t workspace_bytes = 0;
 };
 
 struct mb_block {
@@ -198,6 +203,9 @@ int32_t mb_shutdown(mb_ctx* ctx) {
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    if (ctx->h2d_stream) cudaStreamDestroy(ctx->h2d_stream);
+    if (ctx->d2h_stream) cudaStreamDestroy(ctx->d2h_stream);
+    if (ctx->workspace) cudaFree(ctx->workspace);
     delete ctx;
     return MB_OK;
 }
@@ -496,6 +504,94 @@ int32_t mb_matmul_blocked(mb_ctx* ctx, mb_block* const* A_tiles, mb_block* const
                 int32_t r = mb_block_gemm(ctx, A_tiles[i * k + kk], B_tiles[kk * n + j], C_tiles[i * n + j], kk > 0);
                 if (r) return r;
             }
+    return MB_OK;
+}
+
+int32_t mb_matmul_blocked_host(mb_ctx* ctx, const double* const* A_host, const double* const* B_host, int32_t m,
+                               int32_t k, int32_t n, const int32_t* row_len, const int32_t* k_len, const int32_t* col_len,
+                               double* const* C_host) {
+    MB_CTX(ctx);
+    if (!A_host || !B_host || !C_host || !row_len || !k_len || !col_len || m <= 0 || k <= 0 || n <= 0)
+        return fail(MB_ERR_INVALID_ARG, "mb_matmul_blocked_host: bad argument");
+    if (!ctx->h2d_stream) {
+        MB_CUDA(cudaStreamCreateWithFlags(&ctx->h2d_stream, cudaStreamNonBlocking));
+        MB_CUDA(cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking));
+    }
+    // device layout: every tile gets an even leading dimension and a 256-byte aligned slot (TMA eligibility)
+    auto even = [](int x) { return (x + 1) & ~1; };
+    auto slot = [](size_t bytes) { return (bytes + 255) & ~size_t(255); };
+    std::vector<size_t> offA(m * k), offB(k * n), offC(m * n);
+    size_t total = 0;
+    for (int i = 0; i < m; ++i)
+        for (int kk = 0; kk < k; ++kk) { offA[i * k + kk] = total; total += slot((size_t)even(row_len[i]) * k_len[kk] * 8); }
+    for (int kk = 0; kk < k; ++kk)
+        for (int j = 0; j < n; ++j) { offB[kk * n + j] = total; total += slot((size_t)even(k_len[kk]) * col_len[j] * 8); }
+    for (int i = 0; i < m; ++i)
+        for (int j = 0; j < n; ++j) { offC[i * n + j] = total; total += slot((size_t)even(row_len[i]) * col_len[j] * 8); }
+    if (total > ctx->workspace_bytes) {
+        if (ctx->workspace) { MB_CUDA(cudaDeviceSynchronize()); cudaFree(ctx->workspace); ctx->workspace = nullptr; ctx->workspace_bytes = 0; }
+        MB_CUDA(cudaMalloc(&ctx->workspace, total));
+        ctx->workspace_bytes = total;
+    }
+    char* base = static_cast<char*>(ctx->workspace);
+    std::vector<cudaEvent_t> evA(m * k, nullptr), evB(k * n, nullptr), evC(m * n, nullptr);
+    cudaEvent_t ev_start = nullptr, ev_done = nullptr;
+    int32_t rc = MB_OK;
+    cudaError_t e = cudaSuccess;
+    auto upload = [&](bool isA, int idx, int rows, int cols, const double* host, size_t off, cudaEvent_t& ev) {
+        if (ev || e != cudaSuccess) return;
+        e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+        if (e != cudaSuccess) return;
+        if (rows > 0 && cols > 0)
+            e = cudaMemcpy2DAsync(base + off, (size_t)even(rows) * 8, host, (size_t)rows * 8, (size_t)rows * 8, cols,
+                                  cudaMemcpyHostToDevice, ctx->h2d_stream);
+        if (e == cudaSuccess) e = cudaEventRecord(ev, ctx->h2d_stream);
+        (void)isA; (void)idx;
+    };
+    // the workspace may still be read by a previous call on ctx->stream / d2h_stream: order behind them
+    e = cudaEventCreateWithFlags(&ev_start, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventRecord(ev_start, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->h2d_stream, ev_start, 0);
+    for (int i = 0; i < m && e == cudaSuccess && rc == MB_OK; ++i)
+        for (int j = 0; j < n && e == cudaSuccess && rc == MB_OK; ++j) {
+            for (int kk = 0; kk < k && e == cudaSuccess && rc == MB_OK; ++kk) {
+                // uploads in first-use order (seq = i*n*k + j*k + kk)
+                upload(true, i * k + kk, row_len[i], k_len[kk], A_host[i * k + kk], offA[i * k + kk], evA[i * k + kk]);
+                upload(false, kk * n + j, k_len[kk], col_len[j], B_host[kk * n + j], offB[kk * n + j], evB[kk * n + j]);
+                if (e != cudaSuccess) break;
+                e = cudaStreamWaitEvent(ctx->stream, evA[i * k + kk], 0);
+                if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->stream, evB[kk * n + j], 0);
+                if (e != cudaSuccess) break;
+                rc = dgemm_device_impl(ctx, 'N', 'N', row_len[i], col_len[j], k_len[kk], 1.0,
+                                       reinterpret_cast<double*>(base + offA[i * k + kk]), even(row_len[i]) > 0 ? even(row_len[i]) : 1,
+                                       reinterpret_cast<double*>(base + offB[kk * n + j]), even(k_len[kk]) > 0 ? even(k_len[kk]) : 1,
+                                       kk > 0 ? 1.0 : 0.0, reinterpret_cast<double*>(base + offC[i * n + j]),
+                                       even(row_len[i]) > 0 ? even(row_len[i]) : 1, false);
+            }
+            if (e != cudaSuccess || rc != MB_OK) break;
+            e = cudaEventCreateWithFlags(&evC[i * n + j], cudaEventDisableTiming);
+            if (e == cudaSuccess) e = cudaEventRecord(evC[i * n + j], ctx->stream);
+            if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->d2h_stream, evC[i * n + j], 0);
+            if (e == cudaSuccess && row_len[i] > 0 && col_len[j] > 0)
+                e = cudaMemcpy2DAsync(C_host[i * n + j], (size_t)row_len[i] * 8, base + offC[i * n + j], (size_t)even(row_len[i]) * 8,
+                                      (size_t)row_len[i] * 8, col_len[j], cudaMemcpyDeviceToHost, ctx->d2h_stream);
+        }
+    if (e == cudaSuccess && rc == MB_OK) {
+        // the call returns when every C tile is on the host; ctx->stream is ordered behind the downloads too
+        e = cudaEventCreateWithFlags(&ev_done, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventRecord(ev_done, ctx->d2h_stream);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->stream, ev_done, 0);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->d2h_stream);
+    } else {
+        cudaStreamSynchronize(ctx->h2d_stream); cudaStreamSynchronize(ctx->stream); cudaStreamSynchronize(ctx->d2h_stream);
+    }
+    for (auto ev : evA) if (ev) cudaEventDestroy(ev);
+    for (auto ev : evB) if (ev) cudaEventDestroy(ev);
+    for (auto ev : evC) if (ev) cudaEventDestroy(ev);
+    if (ev_start) cudaEventDestroy(ev_start);
+    if (ev_done) cudaEventDestroy(ev_done);
+    if (rc != MB_OK) return rc;
+    if (e != cudaSuccess) return cuda_fail(e, "mb_matmul_blocked_host");
     return MB_OK;
 }
 
