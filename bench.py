@@ -213,12 +213,17 @@ def run_ours(args):
     ms_step = float(t.item()) / args.steps
     value = flops / (ms_step * 1e-3) / 1e12
 
-    # dominant kernel: the per-block DMMA GEMM (8192^3 at the default size); average launch duration from the
-    # CUDA events bracketing each launch on the launching stream
+    # dominant kernel: the DMMA GEMM.  Average launch duration from the CUDA events bracketing each launch on the
+    # launching stream; algorithmic flops per launch = this rank's share of the 2*N^3 flops / its launches per step
+    # (1 grouped launch when the rank holds whole kk-sums, else one launch per 8192^3 block product).
     bs = N // g
+    plan = comm.plan_multiply(g, g, g, ws, A.owner, B.owner)
+    local_products = len(plan.products.get(rank, []))
     gemm_ms, gemm_n = phases.get("gemm", (0.0, 0))
     gemm_avg_ms = gemm_ms / max(1, gemm_n)
-    achieved = 2.0 * bs ** 3 / (gemm_avg_ms * 1e-3) / 1e12 if gemm_n else None
+    launches_per_step = max(1, gemm_n // max(1, args.steps))
+    flops_per_launch = local_products * 2.0 * bs ** 3 / launches_per_step
+    achieved = flops_per_launch / (gemm_avg_ms * 1e-3) / 1e12 if gemm_n else None
     traffic = None
     summary = ROOT / "profiles" / "ncu_summary.json"
     if summary.exists():
@@ -228,8 +233,8 @@ def run_ours(args):
             traffic = None
     roofline = {"bound": "tensor", "achieved": achieved, "peak": FP64_PEAK_TFLOPS_MEASURED, "unit": "TFLOP/s",
                 "frac": (achieved / FP64_PEAK_TFLOPS_MEASURED) if achieved else None, "traffic": traffic,
-                "kernel": "gemm_f64_dmma_kernel<N,N> (DMMA.8x8x4 + TMA)", "launch_ms_avg": gemm_avg_ms,
-                "flops_per_launch": 2.0 * bs ** 3,
+                "kernel": ("gemm_f64_dmma_grouped_kernel" if launches_per_step < local_products else "gemm_f64_dmma_kernel<N,N>") + " (DMMA.8x8x4 + TMA)", "launch_ms_avg": gemm_avg_ms,
+                "flops_per_launch": flops_per_launch, "launches_per_step": launches_per_step,
                 "peak_source": "measured fp64 DMMA issue peak on this pool's B200 (scripts/dmma_bench.cu, "
                                "profiles/r01_probe_dmma_peak_and_gemm_v1.log); MEASURED_PEAKS.json carries no fp64 entry; "
                                "cuBLAS dgemm on the same GPU measured 36.2 TFLOP/s"}

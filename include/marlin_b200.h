@@ -160,6 +160,12 @@ int32_t mb_block_len(int64_t total, int32_t parts, int32_t* block_len, int32_t* 
  *      (marlin_b200.matrix.BlockMatrix) with one process per GPU. */
 int32_t mb_matmul_blocked(mb_ctx* ctx, mb_block* const* A_tiles, mb_block* const* B_tiles,
                           int32_t m, int32_t k, int32_t n, mb_block* const* C_tiles);
+/* The share of that multiply one rank runs: only the C blocks listed in c_ids (c = i*n + j), each with its full
+ * kk-sum.  Tile slots this rank does not need may be NULL.  fp64 'N' blocks run as ONE persistent grouped launch
+ * (K loop concatenated over kk, no C read-modify-write); anything else falls back to per-product launches. */
+int32_t mb_matmul_blocked_subset(mb_ctx* ctx, mb_block* const* A_tiles, mb_block* const* B_tiles,
+                                 int32_t m, int32_t k, int32_t n, mb_block* const* C_tiles,
+                                 const int32_t* c_ids, int32_t num_c);
 
 /* The same multiply for JVM-held blocks (HOST column-major fp64 arrays in, host arrays out): the entry a
  * `BlockMatrix.multiply` whose SubMatrix data still lives on the heap would bind.  A_host[i*k+kk] is the packed

@@ -491,20 +491,75 @@ int32_t mb_block_gemm(mb_ctx* ctx, const mb_block* A, const mb_block* B, mb_bloc
     return fail(MB_ERR_UNSUPPORTED, "mb_block_gemm: unsupported dtype combination (%d,%d)->%d", A->dtype, B->dtype, C->dtype);
 }
 
+int32_t mb_matmul_blocked_subset(mb_ctx* ctx, mb_block* const* A_tiles, mb_block* const* B_tiles, int32_t m, int32_t k,
+                                 int32_t n, mb_block* const* C_tiles, const int32_t* c_ids, int32_t num_c) {
+    MB_CTX(ctx);
+    if (!A_tiles || !B_tiles || !C_tiles || !c_ids || m <= 0 || k <= 0 || n <= 0 || num_c < 0)
+        return fail(MB_ERR_INVALID_ARG, "mb_matmul_blocked: bad argument");
+    for (int c = 0; c < num_c; ++c) {
+        const int id = c_ids[c];
+        if (id < 0 || id >= m * n || !C_tiles[id]) return fail(MB_ERR_INVALID_ARG, "mb_matmul_blocked: bad C id %d", id);
+        const int i = id / n, j = id % n;
+        for (int kk = 0; kk < k; ++kk) {
+            const mb_block *a = A_tiles[i * k + kk], *b = B_tiles[kk * n + j];
+            if (!a || !b) return fail(MB_ERR_INVALID_ARG, "mb_matmul_blocked: missing tile for C(%d,%d), kk=%d", i, j, kk);
+            if (a->cols != b->rows)
+                return fail(MB_ERR_DIM_MISMATCH, "Dimension mismatch during matrix-matrix multiplication: %d vs %d", a->cols, b->rows);
+            if (C_tiles[id]->rows != a->rows || C_tiles[id]->cols != b->cols)
+                return fail(MB_ERR_DIM_MISMATCH, "mb_matmul_blocked: C(%d,%d) is %dx%d, expected %dx%d", i, j, C_tiles[id]->rows,
+                            C_tiles[id]->cols, a->rows, b->cols);
+        }
+    }
+    // ---- grouped single launch when every operand is an fp64 column-major ('N') block ----
+    bool groupable = num_c > 0;
+    std::vector<const double*> Ap(m * k, nullptr), Bp(k * n, nullptr);
+    std::vector<double*> Cp(m * n, nullptr);
+    std::vector<long long> lda(m * k, 2), ldb(k * n, 2), ldc(m * n, 2);
+    std::vector<int> row_len(m, 1), k_len(k, 1), col_len(n, 1);
+    for (int c = 0; c < num_c && groupable; ++c) {
+        const int id = c_ids[c], i = id / n, j = id % n;
+        const mb_block* cb = C_tiles[id];
+        groupable = cb->dtype == MB_F64 && !cb->is_transpose;
+        Cp[id] = f64_ptr(cb); ldc[id] = cb->ld;
+        for (int kk = 0; kk < k && groupable; ++kk) {
+            const mb_block *a = A_tiles[i * k + kk], *b = B_tiles[kk * n + j];
+            groupable = a->dtype == MB_F64 && b->dtype == MB_F64 && !a->is_transpose && !b->is_transpose && a->rows > 0 &&
+                        a->cols > 0 && b->cols > 0;
+            Ap[i * k + kk] = f64_ptr(a); lda[i * k + kk] = a->ld;
+            Bp[kk * n + j] = f64_ptr(b); ldb[kk * n + j] = b->ld;
+            // the k-slab count is shared by all C blocks: every A(.,kk) must have the same column count
+            if (k_len[kk] != 1 && k_len[kk] != a->cols) groupable = false;
+            k_len[kk] = a->cols;
+            row_len[i] = a->rows; col_len[j] = b->cols;
+        }
+    }
+    if (groupable) {
+        int launches = 0;
+        cudaError_t e = mb::gemm_f64_grouped(m, k, n, c_ids, num_c, Ap.data(), lda.data(), Bp.data(), ldb.data(), Cp.data(),
+                                             ldc.data(), row_len.data(), k_len.data(), col_len.data(), ctx->num_sms, ctx->stream,
+                                             &launches);
+        if (e == cudaSuccess) { ctx->launches += launches; return MB_OK; }
+        if (e != cudaErrorNotSupported) return cuda_fail(e, "gemm_f64_grouped");
+        cudaGetLastError();
+    }
+    // ---- fallback: seq order of matrix/BlockMatrix.scala:163,168 (p = i*n*k + j*k + kk), the kk partials of C(i,j)
+    //      (reduceByKey at :177) accumulated in place, kk ascending ----
+    for (int c = 0; c < num_c; ++c) {
+        const int id = c_ids[c], i = id / n, j = id % n;
+        for (int kk = 0; kk < k; ++kk) {
+            int32_t r = mb_block_gemm(ctx, A_tiles[i * k + kk], B_tiles[kk * n + j], C_tiles[id], kk > 0);
+            if (r) return r;
+        }
+    }
+    return MB_OK;
+}
+
 int32_t mb_matmul_blocked(mb_ctx* ctx, mb_block* const* A_tiles, mb_block* const* B_tiles, int32_t m, int32_t k,
                           int32_t n, mb_block* const* C_tiles) {
-    MB_CTX(ctx);
-    if (!A_tiles || !B_tiles || !C_tiles || m <= 0 || k <= 0 || n <= 0)
-        return fail(MB_ERR_INVALID_ARG, "mb_matmul_blocked: bad argument");
-    // seq order of matrix/BlockMatrix.scala:163,168: p = i*n*k + j*k + kk; the kk partials of C(i,j)
-    // (reduceByKey at :177) are accumulated in place, kk ascending.
-    for (int i = 0; i < m; ++i)
-        for (int j = 0; j < n; ++j)
-            for (int kk = 0; kk < k; ++kk) {
-                int32_t r = mb_block_gemm(ctx, A_tiles[i * k + kk], B_tiles[kk * n + j], C_tiles[i * n + j], kk > 0);
-                if (r) return r;
-            }
-    return MB_OK;
+    if (m <= 0 || k <= 0 || n <= 0) return fail(MB_ERR_INVALID_ARG, "mb_matmul_blocked: bad argument");
+    std::vector<int32_t> ids(m * n);
+    for (int c = 0; c < m * n; ++c) ids[c] = c;
+    return mb_matmul_blocked_subset(ctx, A_tiles, B_tiles, m, k, n, C_tiles, ids.data(), m * n);
 }
 
 int32_t mb_matmul_blocked_host(mb_ctx* ctx, const double* const* A_host, const double* const* B_host, int32_t m,

@@ -252,6 +252,172 @@ gemm_f64_dmma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
 }
 
 // -------------------------------------------------------------------------------------------
+// Grouped variant: ONE persistent launch for a whole blocked multiply on this GPU
+// (BlockMatrix.multiply, matrix/BlockMatrix.scala:149-186): the CTA-tile list spans every C block (i,j) this rank
+// owns, and each CTA-tile runs its K loop over the concatenation kk = 0..k-1 of A(i,kk) / B(kk,j), i.e. the
+// reduceByKey over kk (:177) happens in the register accumulators.  Compared with one launch per block product
+// this removes the per-launch tail (4096 tiles on 148 SMs = 27.7 waves) and the C read-modify-write of accumulate.
+// All operands are 'N' (column-major blocks).
+// -------------------------------------------------------------------------------------------
+constexpr int GROUP_MAX_A = 16, GROUP_MAX_B = 16, GROUP_MAX_C = 16, GROUP_MAX_K = 16;
+
+struct GroupedParams {
+    CUtensorMap mapA[GROUP_MAX_A];     // index a_idx[c] + kk   (the A block row of C block c, kk ascending)
+    CUtensorMap mapB[GROUP_MAX_B];     // index b_idx[c] + kk
+    double* C[GROUP_MAX_C];
+    long long ldc[GROUP_MAX_C];
+    int M[GROUP_MAX_C], N[GROUP_MAX_C];
+    int a_idx[GROUP_MAX_C], b_idx[GROUP_MAX_C];
+    int tile_start[GROUP_MAX_C + 1];   // prefix sum of CTA-tiles per C block
+    int tiles_m[GROUP_MAX_C], tiles_n[GROUP_MAX_C];
+    int num_c, k;
+    int num_kb[GROUP_MAX_K];           // k-slabs of segment kk
+};
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_f64_dmma_grouped_kernel(const __grid_constant__ GroupedParams g) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bar_full = smem_base + NUM_STAGES * STAGE_BYTES;
+    const uint32_t bar_empty = bar_full + NUM_STAGES * 8;
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int num_tiles = g.tile_start[g.num_c];
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NUM_STAGES; ++s) {
+            mbar_init(bar_full + 8 * s, 1);
+            mbar_init(bar_empty + 8 * s, NUM_CONSUMER_WARPS);
+        }
+        fence_barrier_init();
+    }
+    __syncthreads();
+
+    auto locate = [&](int t, int& c, int& tm, int& tn) {
+        c = 0;
+        while (t >= g.tile_start[c + 1]) ++c;
+        tile_coords(t - g.tile_start[c], g.tiles_m[c], g.tiles_n[c], tm, tn);
+    };
+
+    if (warp < 4) {
+        setmaxnreg_dec<40>();
+        if (warp == 0 && lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+                int c, tm, tn;
+                locate(t, c, tm, tn);
+                const int m0 = tm * BM, n0 = tn * BN;
+                for (int kk = 0; kk < g.k; ++kk) {
+                    const CUtensorMap* mA = &g.mapA[g.a_idx[c] + kk];
+                    const CUtensorMap* mB = &g.mapB[g.b_idx[c] + kk];
+                    const int nkb = g.num_kb[kk];
+                    for (int kb = 0; kb < nkb; ++kb) {
+                        mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+                        const uint32_t full = bar_full + 8 * stage;
+                        const uint32_t sA = smem_base + stage * STAGE_BYTES;
+                        const uint32_t sB = sA + OPERAND_BYTES;
+                        mbar_arrive_expect_tx(full, STAGE_BYTES);
+                        const int k0 = kb * BK;
+#pragma unroll
+                        for (int b = 0; b < 8; ++b) tma_load_2d(sA + b * 2048, mA, full, m0 + 16 * b, k0);
+                        tma_load_2d(sB, mB, full, k0, n0);
+                        if (++stage == NUM_STAGES) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+        return;
+    }
+
+    setmaxnreg_inc<232>();
+    const int cw = warp - 4;
+    const int warp_m = cw & 1;
+    const int warp_n = cw >> 1;
+    const int r = lane >> 2;
+    const int q = lane & 3;
+    const int pr = perm8(r);
+    uint32_t offA[2][2], offB[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+#pragma unroll
+        for (int pp = 0; pp < 2; ++pp) {
+            const int krow = 8 * h + 2 * q + pp;
+            offA[h][pp] = warp_m * 4 * 2048 + krow * 128 + ((r ^ (krow & 7)) << 4);
+        }
+        offB[h] = warp_n * 32 * 128 + pr * 128 + ((((4 * h + q) ^ pr) & 7) << 4);
+    }
+    int total_kb = 0;
+    for (int kk = 0; kk < g.k; ++kk) total_kb += g.num_kb[kk];
+
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        int c, tm_, tn_;
+        locate(t, c, tm_, tn_);
+        const int m0 = tm_ * BM, n0 = tn_ * BN;
+        double acc[8][4][2];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+        for (int kb = 0; kb < total_kb; ++kb) {
+            mbar_wait(bar_full + 8 * stage, phase);
+            const uint32_t sA = smem_base + stage * STAGE_BYTES;
+            const uint32_t sB = sA + OPERAND_BYTES;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                double a[8][2], b[4][2];
+#pragma unroll
+                for (int tp = 0; tp < 4; ++tp)
+#pragma unroll
+                    for (int pp = 0; pp < 2; ++pp) lds128(a[2 * tp][pp], a[2 * tp + 1][pp], sA + offA[h][pp] + tp * 2048);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) lds128(b[u][0], b[u][1], sB + offB[h] + u * 8 * 128);
+                if (h == 1) {
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_empty + 8 * stage);
+                }
+#pragma unroll
+                for (int pp = 0; pp < 2; ++pp)
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], a[i][pp], b[j][pp]);
+            }
+            if (++stage == NUM_STAGES) { stage = 0; phase ^= 1; }
+        }
+
+        double* Cb = g.C[c];
+        const long long ldc = g.ldc[c];
+        const int Mc = g.M[c], Nc = g.N[c];
+        const bool vec_ok = ((reinterpret_cast<uintptr_t>(Cb) & 15) == 0) && ((ldc & 1) == 0);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+#pragma unroll
+            for (int jj = 0; jj < 2; ++jj) {
+                const int n = n0 + warp_n * 32 + 8 * j + perm8(2 * q + jj);
+                if (n >= Nc) continue;
+                double* ccol = Cb + (long long)n * ldc;
+#pragma unroll
+                for (int tp = 0; tp < 4; ++tp) {
+                    const int m = m0 + warp_m * 64 + 16 * tp + 2 * r;
+                    if (m >= Mc) continue;
+                    const double v0 = acc[2 * tp][j][jj], v1 = acc[2 * tp + 1][j][jj];
+                    if (vec_ok && m + 1 < Mc) {
+                        *reinterpret_cast<double2*>(ccol + m) = make_double2(v0, v1);
+                    } else {
+                        ccol[m] = v0;
+                        if (m + 1 < Mc) ccol[m + 1] = v1;
+                    }
+                }
+            }
+        }
+    }
+}
+
+// -------------------------------------------------------------------------------------------
 // Generic CUDA-core kernel: any ld / offset / alignment, any trans.  64x64 tile, 4x4 per thread.
 // Used when TMA's 16-byte rules do not hold (odd leading dimension or odd element offset of a
 // Breeze view) and as an independent on-device cross-check in the tests.
@@ -416,6 +582,71 @@ cudaError_t gemm_f64(bool transA, bool transB, int M, int N, int K, double alpha
         gemm_f64_generic_kernel<false, true><<<grid, 256, 0, stream>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
     else
         gemm_f64_generic_kernel<true, true><<<grid, 256, 0, stream>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
+    return cudaGetLastError();
+}
+
+
+cudaError_t gemm_f64_grouped(int m, int k, int n, const int* my_c, int num_c, const double* const* A, const long long* lda,
+                             const double* const* B, const long long* ldb, double* const* C, const long long* ldc,
+                             const int* row_len, const int* k_len, const int* col_len, int num_sms, cudaStream_t stream,
+                             int* launches) {
+    // my_c: the (i*n + j) ids of the C blocks to compute; A[i*k+kk], B[kk*n+j], C[i*n+j] column-major 'N' blocks
+    if (num_c <= 0) return cudaSuccess;
+    if (num_c > GROUP_MAX_C || k > GROUP_MAX_K || !get_encode_fn()) return cudaErrorNotSupported;
+    static thread_local GroupedParams g;     // ~4.6 KB parameter block: kept off the stack, one per calling thread
+    int na = 0, nb = 0;
+    int a_of_row[GROUP_MAX_C], b_of_col[GROUP_MAX_C];
+    int rows_seen[GROUP_MAX_C], cols_seen[GROUP_MAX_C], nrows = 0, ncols = 0;
+    g.num_c = num_c;
+    g.k = k;
+    for (int kk = 0; kk < k; ++kk) {
+        if (k_len[kk] <= 0) return cudaErrorNotSupported;
+        g.num_kb[kk] = (k_len[kk] + BK - 1) / BK;
+    }
+    g.tile_start[0] = 0;
+    for (int c = 0; c < num_c; ++c) {
+        const int i = my_c[c] / n, j = my_c[c] % n;
+        if (row_len[i] <= 0 || col_len[j] <= 0) return cudaErrorNotSupported;
+        int ri = -1, cj = -1;
+        for (int x = 0; x < nrows; ++x) if (rows_seen[x] == i) ri = x;
+        for (int x = 0; x < ncols; ++x) if (cols_seen[x] == j) cj = x;
+        if (ri < 0) {
+            if (na + k > GROUP_MAX_A) return cudaErrorNotSupported;
+            for (int kk = 0; kk < k; ++kk) {
+                const double* Ap = A[i * k + kk];
+                if (!gemm_f64_tma_eligible(Ap, lda[i * k + kk], Ap, 2)) return cudaErrorNotSupported;
+                if (!make_map_f64(&g.mapA[na + kk], Ap, row_len[i], k_len[kk], lda[i * k + kk], 16, 16)) return cudaErrorNotSupported;
+            }
+            rows_seen[nrows] = i; a_of_row[nrows] = na; ri = nrows++; na += k;
+        }
+        if (cj < 0) {
+            if (nb + k > GROUP_MAX_B) return cudaErrorNotSupported;
+            for (int kk = 0; kk < k; ++kk) {
+                const double* Bp = B[kk * n + j];
+                if (!gemm_f64_tma_eligible(Bp, ldb[kk * n + j], Bp, 2)) return cudaErrorNotSupported;
+                if (!make_map_f64(&g.mapB[nb + kk], Bp, k_len[kk], col_len[j], ldb[kk * n + j], 16, 128)) return cudaErrorNotSupported;
+            }
+            cols_seen[ncols] = j; b_of_col[ncols] = nb; cj = ncols++; nb += k;
+        }
+        g.a_idx[c] = a_of_row[ri];
+        g.b_idx[c] = b_of_col[cj];
+        g.C[c] = C[my_c[c]];
+        g.ldc[c] = ldc[my_c[c]];
+        g.M[c] = row_len[i];
+        g.N[c] = col_len[j];
+        g.tiles_m[c] = (row_len[i] + BM - 1) / BM;
+        g.tiles_n[c] = (col_len[j] + BN - 1) / BN;
+        g.tile_start[c + 1] = g.tile_start[c] + g.tiles_m[c] * g.tiles_n[c];
+    }
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(gemm_f64_dmma_grouped_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+        attr_done = true;
+    }
+    const int grid = min(g.tile_start[num_c], num_sms);
+    gemm_f64_dmma_grouped_kernel<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(g);
+    if (launches) ++*launches;
     return cudaGetLastError();
 }
 

@@ -229,13 +229,37 @@ class BlockMatrix(DistributedMatrix):
                 (a_tiles if key[0] == "A" else b_tiles)[key[1:]] = SubMatrix(buf=buf, rows=r, cols=c, ld=max(1, r))
         # the join + one dgemm per partition (:173-176), kk-partials of a C tile accumulated in place (:177)
         partial: Dict[Tuple[int, int], SubMatrix] = {}
-        for (i, j, kk) in plan.products.get(rank, []):
-            a, b = a_tiles[(i, kk)], b_tiles[(kk, j)]
+        mine = plan.products.get(rank, [])
+        by_c: Dict[Tuple[int, int], List[int]] = {}
+        for (i, j, kk) in mine:
+            by_c.setdefault((i, j), []).append(kk)
+        whole = bool(by_c) and all(sorted(v) == list(range(k)) for v in by_c.values())
+        if whole and len(by_c) <= 16 and k <= 16:
+            # this rank holds every kk of its C tiles: ONE grouped persistent launch (K loop concatenated over kk)
+            import ctypes as C
+            rt = Runtime.get(); rt.sync_stream()
+            a_arr = (nat.c_blk * (m * k))()
+            b_arr = (nat.c_blk * (k * n))()
+            c_arr = (nat.c_blk * (m * n))()
+            for (i, j) in by_c:
+                for kk in range(k):
+                    a_arr[i * k + kk] = a_tiles[(i, kk)].handle()
+                    b_arr[kk * n + j] = b_tiles[(kk, j)].handle()
+                a0, b0 = a_tiles[(i, 0)], b_tiles[(0, j)]
+                out_dt = nat.MB_F32 if a0.dtype == nat.MB_BF16 else a0.dtype
+                partial[(i, j)] = SubMatrix.empty(a0.rows, b0.cols, out_dt, a0.buf.device)
+                c_arr[i * n + j] = partial[(i, j)].handle()
+            ids = (C.c_int32 * len(by_c))(*[i * n + j for (i, j) in sorted(by_c)])
             with profiling.phase("gemm"):
-                if (i, j) in partial:
-                    a.multiply(b, out=partial[(i, j)], accumulate=True)
-                else:
-                    partial[(i, j)] = a.multiply(b)
+                nat.check(rt.lib.mb_matmul_blocked_subset(rt.ctx, a_arr, b_arr, m, k, n, c_arr, ids, len(by_c)))
+        else:
+            for (i, j, kk) in mine:
+                a, b = a_tiles[(i, kk)], b_tiles[(kk, j)]
+                with profiling.phase("gemm"):
+                    if (i, j) in partial:
+                        a.multiply(b, out=partial[(i, j)], accumulate=True)
+                    else:
+                        partial[(i, j)] = a.multiply(b)
         if ws > 1 and plan.c_reduces:
             # reduceByKey across ranks (:177): partials travel to the C tile's owner and are added there
             sends = [(s, d, ("C",) + key + (s,)) for s, d, key in plan.c_reduces]
