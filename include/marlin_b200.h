@@ -178,6 +178,21 @@ int32_t mb_matmul_blocked_host(mb_ctx* ctx, const double* const* A_host, const d
                                int32_t m, int32_t k, int32_t n, const int32_t* row_len, const int32_t* k_len,
                                const int32_t* col_len, double* const* C_host);
 
+/* ---- peer memory: NVLink P2P between the per-GPU processes of one box (CUDA IPC) ------------------------------
+ * Replaces the shuffle transport of the multiply (matrix/BlockMatrix.scala:161-177): a rank maps the tile buffers
+ * of the others once, pulls the tiles it needs with copy-engine DMA (mb_memcpy_async on a side stream) and lets its
+ * GEMM epilogue store partial products directly into the reducing rank's memory (pass a peer pointer as C).
+ * Ordering between processes uses stream-ordered flags (monotonic epochs) living in exported device memory. */
+int32_t mb_ipc_export(mb_ctx* ctx, const void* device_ptr, uint8_t handle_out[64], int64_t* offset_out,
+                      int64_t* alloc_bytes_out);
+int32_t mb_ipc_open(mb_ctx* ctx, const uint8_t handle[64], void** base_out);     /* cached per handle */
+int32_t mb_ipc_close_all(mb_ctx* ctx);
+int32_t mb_flags_alloc(mb_ctx* ctx, int32_t count, void** flags_out);            /* zeroed uint64[count], cudaMalloc'd */
+int32_t mb_flags_free(mb_ctx* ctx, void* flags);
+int32_t mb_flag_signal(mb_ctx* ctx, void* flag, int64_t value);   /* on the ctx stream: release-store (system scope) */
+int32_t mb_flag_wait(mb_ctx* ctx, const void* flag, int64_t value); /* on the ctx stream: wait until *flag >= value */
+int32_t mb_memcpy_async(mb_ctx* ctx, void* dst, const void* src, int64_t bytes);   /* D2D (local or peer) on the ctx stream */
+
 /* ---- rows <-> blocks on device (matrix/DenseVecMatrix.scala:1084-1223, 1259-1328;
  *      matrix/BlockMatrix.scala:575-594): a DenseVecMatrix shard is a row-major (rows x cols)
  *      buffer, i.e. a transposed block; these are strided copies (mb_block_copy on views). */

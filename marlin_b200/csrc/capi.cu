@@ -40,6 +40,14 @@ struct mb_block {
     int device = 0;
 };
 
+namespace mb {
+cudaError_t ipc_export(const void* dptr, unsigned char handle[64], long long* offset, long long* alloc_bytes);
+cudaError_t ipc_open(const unsigned char handle[64], void** base_out);
+cudaError_t ipc_close_all();
+cudaError_t flag_signal(void* flag, unsigned long long v, cudaStream_t st);
+cudaError_t flag_wait(const void* flag, unsigned long long v, cudaStream_t st);
+}  // namespace mb
+
 namespace {
 
 thread_local char g_err[512] = "";
@@ -99,14 +107,22 @@ int32_t binary_op(mb_ctx* ctx, int op, const mb_block* A, const mb_block* B, mb_
     if (r) return r;
     r = same_shape(A, out, name);
     if (r) return r;
-    if (A->dtype != MB_F64 || B->dtype != MB_F64 || out->dtype != MB_F64)
-        return fail(MB_ERR_UNSUPPORTED, "%s: fp64 blocks only (convert bf16 blocks with mb_block_copy)", name);
+    const bool all_f32 = A->dtype == MB_F32 && B->dtype == MB_F32 && out->dtype == MB_F32;
+    if (!all_f32 && (A->dtype != MB_F64 || B->dtype != MB_F64 || out->dtype != MB_F64))
+        return fail(MB_ERR_UNSUPPORTED, "%s: fp64 (or all-fp32) blocks only (convert bf16 blocks with mb_block_copy)", name);
     // iterate in the output's storage order so the store side is contiguous
     int rows = A->rows, cols = A->cols;
     long long ars = rs(A), acs = cs(A), brs = rs(B), bcs = cs(B), ors = rs(out), ocs = cs(out);
     if (out->is_transpose) {
         std::swap(rows, cols);
         std::swap(ars, acs); std::swap(brs, bcs); std::swap(ors, ocs);
+    }
+    if (all_f32) {
+        MB_CUDA(mb::ew_binary_f32(op, rows, cols, reinterpret_cast<const float*>(elem_ptr(A)), ars, acs,
+                                  reinterpret_cast<const float*>(elem_ptr(B)), brs, bcs, reinterpret_cast<float*>(elem_ptr(out)), ors,
+                                  ocs, ctx->stream));
+        ctx->launches++;
+        return MB_OK;
     }
     MB_CUDA(mb::ew_binary(op, rows, cols, f64_ptr(A), ars, acs, f64_ptr(B), brs, bcs, f64_ptr(out), ors, ocs, ctx->stream));
     ctx->launches++;
@@ -647,6 +663,63 @@ int32_t mb_matmul_blocked_host(mb_ctx* ctx, const double* const* A_host, const d
     if (ev_done) cudaEventDestroy(ev_done);
     if (rc != MB_OK) return rc;
     if (e != cudaSuccess) return cuda_fail(e, "mb_matmul_blocked_host");
+    return MB_OK;
+}
+
+// ----------------------------------------------------------------------------- peer memory
+int32_t mb_ipc_export(mb_ctx* ctx, const void* device_ptr, uint8_t handle_out[64], int64_t* offset_out, int64_t* alloc_bytes_out) {
+    MB_CTX(ctx);
+    if (!device_ptr || !handle_out || !offset_out || !alloc_bytes_out) return fail(MB_ERR_INVALID_ARG, "mb_ipc_export: null argument");
+    long long off = 0, bytes = 0;
+    MB_CUDA(mb::ipc_export(device_ptr, handle_out, &off, &bytes));
+    *offset_out = off; *alloc_bytes_out = bytes;
+    return MB_OK;
+}
+int32_t mb_ipc_open(mb_ctx* ctx, const uint8_t handle[64], void** base_out) {
+    MB_CTX(ctx);
+    if (!handle || !base_out) return fail(MB_ERR_INVALID_ARG, "mb_ipc_open: null argument");
+    MB_CUDA(mb::ipc_open(handle, base_out));
+    return MB_OK;
+}
+int32_t mb_ipc_close_all(mb_ctx* ctx) {
+    MB_CTX(ctx);
+    MB_CUDA(cudaDeviceSynchronize());
+    MB_CUDA(mb::ipc_close_all());
+    return MB_OK;
+}
+int32_t mb_flags_alloc(mb_ctx* ctx, int32_t count, void** flags_out) {
+    MB_CTX(ctx);
+    if (count <= 0 || !flags_out) return fail(MB_ERR_INVALID_ARG, "mb_flags_alloc: bad argument");
+    // a private cudaMalloc (not a sub-allocation of somebody's pool), so the exported handle maps exactly this array
+    MB_CUDA(cudaMalloc(flags_out, sizeof(unsigned long long) * (size_t)count));
+    MB_CUDA(cudaMemset(*flags_out, 0, sizeof(unsigned long long) * (size_t)count));
+    MB_CUDA(cudaDeviceSynchronize());
+    return MB_OK;
+}
+int32_t mb_flags_free(mb_ctx* ctx, void* flags) {
+    MB_CTX(ctx);
+    if (flags) cudaFree(flags);
+    return MB_OK;
+}
+int32_t mb_flag_signal(mb_ctx* ctx, void* flag, int64_t value) {
+    MB_CTX(ctx);
+    if (!flag) return fail(MB_ERR_INVALID_ARG, "mb_flag_signal: null flag");
+    MB_CUDA(mb::flag_signal(flag, (unsigned long long)value, ctx->stream));
+    ctx->launches++;
+    return MB_OK;
+}
+int32_t mb_flag_wait(mb_ctx* ctx, const void* flag, int64_t value) {
+    MB_CTX(ctx);
+    if (!flag) return fail(MB_ERR_INVALID_ARG, "mb_flag_wait: null flag");
+    MB_CUDA(mb::flag_wait(flag, (unsigned long long)value, ctx->stream));
+    ctx->launches++;
+    return MB_OK;
+}
+int32_t mb_memcpy_async(mb_ctx* ctx, void* dst, const void* src, int64_t bytes) {
+    MB_CTX(ctx);
+    if (bytes < 0 || (bytes > 0 && (!dst || !src))) return fail(MB_ERR_INVALID_ARG, "mb_memcpy_async: bad argument");
+    if (bytes == 0) return MB_OK;
+    MB_CUDA(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDeviceToDevice, ctx->stream));
     return MB_OK;
 }
 

@@ -102,6 +102,19 @@ __global__ void unary_strided_kernel(int op, int rows, int cols, const double* a
     }
 }
 
+// fp32 blocks (the C tiles of the bf16 path): same operators, strided form only
+__global__ void binary_strided_f32_kernel(int op, int rows, int cols, const float* a, long long ars, long long acs,
+                                          const float* b, long long brs, long long bcs, float* o, long long ors,
+                                          long long ocs) {
+    const long long total = (long long)rows * cols;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
+         e += (long long)gridDim.x * blockDim.x) {
+        const long long r = e % rows, c = e / rows;
+        const float x = a[r * ars + c * acs], y = b[r * brs + c * bcs];
+        o[r * ors + c * ocs] = (op == EW_ADD) ? __fadd_rn(x, y) : (op == EW_SUB) ? __fsub_rn(x, y) : __fmul_rn(x, y);
+    }
+}
+
 // ---- transpose: out (cols x rows, ldo) = in (rows x cols, ldi)^T, both column-major ----
 // 64x64 tile = 32x32 micro-blocks of 2x2 doubles.  Each thread loads a 2x2 micro-block with two
 // 128-bit loads (two adjacent columns), transposes it in registers, parks it in shared memory and a
@@ -320,6 +333,14 @@ cudaError_t ew_binary(int op, int rows, int cols, const double* a, long long ars
     } else {
         binary_strided_kernel<<<ew_grid(total), EW_THREADS, 0, st>>>(op, rows, cols, a, ars, acs, b, brs, bcs, o, ors, ocs);
     }
+    return cudaGetLastError();
+}
+
+cudaError_t ew_binary_f32(int op, int rows, int cols, const float* a, long long ars, long long acs, const float* b,
+                          long long brs, long long bcs, float* o, long long ors, long long ocs, cudaStream_t st) {
+    if (rows <= 0 || cols <= 0) return cudaSuccess;
+    binary_strided_f32_kernel<<<ew_grid((long long)rows * cols), EW_THREADS, 0, st>>>(op, rows, cols, a, ars, acs, b, brs, bcs, o,
+                                                                                    ors, ocs);
     return cudaGetLastError();
 }
 

@@ -9,6 +9,8 @@ enum { EW_AXPB = 10, EW_DIV = 11, EW_RDIV = 12, EW_COPY = 13 };   // unary ops
 // A view's element (r,c) lives at base[r*rs + c*cs]  (col-major: rs=1, cs=ld; transposed view: rs=ld, cs=1).
 cudaError_t ew_binary(int op, int rows, int cols, const double* a, long long ars, long long acs, const double* b,
                       long long brs, long long bcs, double* o, long long ors, long long ocs, cudaStream_t st);
+cudaError_t ew_binary_f32(int op, int rows, int cols, const float* a, long long ars, long long acs, const float* b,
+                          long long brs, long long bcs, float* o, long long ors, long long ocs, cudaStream_t st);
 cudaError_t ew_unary(int op, int rows, int cols, const double* a, long long ars, long long acs, double* o,
                      long long ors, long long ocs, double alpha, double beta, cudaStream_t st);
 // out (cols x rows, ldo) = in (rows x cols, ldi)^T, both column-major

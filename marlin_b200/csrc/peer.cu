@@ -1,0 +1,97 @@
+// Peer-memory plumbing for the multi-GPU multiply (one process per GPU on one NVSwitch box):
+// CUDA IPC mapping of another rank's device buffers, stream-ordered flags in (peer) device memory, and DMA
+// copies.  With these the tile replication of BlockMatrix.multiply (matrix/BlockMatrix.scala:161-171) becomes
+// copy-engine pulls over NVLink that overlap the first GEMM chunks, and the partial products of the reduceByKey
+// (:177) are written by the GEMM epilogue straight into the reducing rank's HBM (P2P stores), with no NCCL call
+// on the data path.
+#include "../../include/marlin_b200.h"
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+
+namespace mb {
+
+namespace {
+
+__global__ void flag_signal_kernel(unsigned long long* flag, unsigned long long v) {
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(flag), "l"(v) : "memory");
+}
+__global__ void flag_wait_kernel(const unsigned long long* flag, unsigned long long v) {
+    unsigned long long cur;
+    for (;;) {
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(cur) : "l"(flag) : "memory");
+        if (cur >= v) break;
+        __nanosleep(256);
+    }
+}
+
+std::mutex g_mu;
+std::map<std::string, void*> g_opened;     // IPC handle bytes -> mapped base address (per process)
+
+typedef CUresult (*GetRangeFn)(CUdeviceptr*, size_t*, CUdeviceptr);
+GetRangeFn get_range_fn() {
+    static GetRangeFn fn = nullptr;
+    if (!fn) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<GetRangeFn>(ptr);
+    }
+    return fn;
+}
+
+}  // namespace
+
+cudaError_t ipc_export(const void* dptr, unsigned char handle[64], long long* offset, long long* alloc_bytes) {
+    GetRangeFn fn = get_range_fn();
+    if (!fn) return cudaErrorNotSupported;
+    CUdeviceptr base = 0;
+    size_t size = 0;
+    if (fn(&base, &size, reinterpret_cast<CUdeviceptr>(dptr)) != CUDA_SUCCESS) return cudaErrorInvalidValue;
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, reinterpret_cast<void*>(base));
+    if (e != cudaSuccess) return e;
+    static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    std::memcpy(handle, &h, 64);
+    *offset = static_cast<long long>(reinterpret_cast<CUdeviceptr>(dptr) - base);
+    *alloc_bytes = static_cast<long long>(size);
+    return cudaSuccess;
+}
+
+cudaError_t ipc_open(const unsigned char handle[64], void** base_out) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    std::string key(reinterpret_cast<const char*>(handle), 64);
+    auto it = g_opened.find(key);
+    if (it != g_opened.end()) { *base_out = it->second; return cudaSuccess; }
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle, 64);
+    void* base = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) return e;
+    g_opened[key] = base;
+    *base_out = base;
+    return cudaSuccess;
+}
+
+cudaError_t ipc_close_all() {
+    std::lock_guard<std::mutex> lk(g_mu);
+    for (auto& kv : g_opened) cudaIpcCloseMemHandle(kv.second);
+    g_opened.clear();
+    return cudaSuccess;
+}
+
+cudaError_t flag_signal(void* flag, unsigned long long v, cudaStream_t st) {
+    flag_signal_kernel<<<1, 1, 0, st>>>(static_cast<unsigned long long*>(flag), v);
+    return cudaGetLastError();
+}
+cudaError_t flag_wait(const void* flag, unsigned long long v, cudaStream_t st) {
+    flag_wait_kernel<<<1, 1, 0, st>>>(static_cast<const unsigned long long*>(flag), v);
+    return cudaGetLastError();
+}
+
+}  // namespace mb

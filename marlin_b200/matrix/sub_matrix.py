@@ -255,3 +255,47 @@ class SubMatrix:
 
     def __repr__(self):
         return f"SubMatrix({self._rows}x{self._cols}, ld={self.ld}, t={self.is_transpose}, {self.buf.dtype}, {self.buf.device})"
+
+
+class RawBlock:
+    """A column-major block at a raw device address that torch does not own — e.g. a staging slot in ANOTHER rank's HBM
+    mapped through CUDA IPC.  Only usable as a GEMM output (`SubMatrix.multiply(..., out=RawBlock)`)."""
+
+    def __init__(self, ptr: int, rows: int, cols: int, ld: int, dtype: int):
+        self.ptr, self._rows, self._cols, self.ld, self._dtype = int(ptr), int(rows), int(cols), int(ld), int(dtype)
+        self._handle = None
+
+    @property
+    def rows(self) -> int:
+        return self._rows
+
+    @property
+    def cols(self) -> int:
+        return self._cols
+
+    @property
+    def dtype(self) -> int:
+        return self._dtype
+
+    def slice(self, r0: int, r1: int, c0: int, c1: int) -> "RawBlock":
+        esz = 8 if self._dtype == nat.MB_F64 else (4 if self._dtype == nat.MB_F32 else 2)
+        return RawBlock(self.ptr + (r0 + c0 * self.ld) * esz, r1 - r0, c1 - c0, self.ld, self._dtype)
+
+    def handle(self):
+        if self._handle is None:
+            rt = Runtime.get()
+            h = nat.c_blk()
+            nat.check(rt.lib.mb_block_wrap(rt.ctx, C.c_void_p(self.ptr), 0, self._rows, self._cols, self.ld, 0, self._dtype,
+                                           C.byref(h)))
+            self._handle = h
+        return self._handle
+
+    def __del__(self):
+        h = getattr(self, "_handle", None)
+        if h is not None:
+            try:
+                rt = Runtime._instance
+                if rt is not None:
+                    rt.lib.mb_block_free(rt.ctx, h)
+            except Exception:
+                pass
