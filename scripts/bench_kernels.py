@@ -1,0 +1,92 @@
+"""Secondary kernel benchmarks (1 GPU): HBM-bound block kernels vs the measured copy bandwidth, and the bf16 tcgen05
+GEMM vs cuBLAS.  Prints one JSON document; bench.py stays the headline (fp64 multiply)."""
+import ctypes as C
+import json
+import sys
+from pathlib import Path
+
+import torch
+
+ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT))
+import marlin_b200 as mb
+from marlin_b200 import _native as nat
+
+peaks = {}
+try:
+    peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
+except Exception:
+    pass
+HBM = float(peaks.get("hbm_gbs", 6650.0))
+BF16 = float(peaks.get("bf16_tflops", 1590.0))
+rt = mb.Runtime.get()
+out = {"hbm_peak_gbs": HBM, "bf16_peak_tflops": BF16, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback (B200_PROFILING.md)"}
+
+
+def timeit(fn, iters=10, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+hbm = {}
+for n in (8192, 16384):
+    A = mb.MTUtils.randomBlockMatrix(None, n, n, 1, 1, seed=1).blocks[0][1]
+    B = mb.MTUtils.randomBlockMatrix(None, n, n, 1, 1, seed=2).blocks[0][1]
+    O = mb.SubMatrix.empty(n, n)
+    T = mb.SubMatrix.empty(n, n)
+    lib, ctx = rt.lib, rt.ctx
+    rt.sync_stream()
+    elems = n * n
+    cases = {
+        "add (3*8 B/elem)": (lambda: nat.check(lib.mb_block_add(ctx, A.handle(), B.handle(), O.handle())), 24),
+        "axpb (2*8 B/elem)": (lambda: nat.check(lib.mb_block_axpb(ctx, A.handle(), 2.0, 1.0, O.handle())), 16),
+        "transpose (2*8 B/elem)": (lambda: nat.check(lib.mb_block_transpose(ctx, A.handle(), T.handle())), 16),
+        "copy (2*8 B/elem)": (lambda: nat.check(lib.mb_block_copy(ctx, A.handle(), O.handle())), 16),
+        "fill_uniform (8 B/elem)": (lambda: nat.check(lib.mb_fill_uniform(ctx, O.handle(), 7, 0, 0.0, 1.0, 0)), 8),
+    }
+    res = {}
+    for name, (fn, bpe) in cases.items():
+        ms = timeit(fn)
+        gbs = elems * bpe / ms / 1e6
+        res[name] = {"ms": ms, "GB/s": gbs, "frac_of_measured_hbm": gbs / HBM}
+    s = C.c_double()
+    ms = timeit(lambda: nat.check(lib.mb_block_sum(ctx, A.handle(), C.byref(s))))
+    res["sum (8 B/elem, incl. D2H of the scalar)"] = {"ms": ms, "GB/s": elems * 8 / ms / 1e6, "frac_of_measured_hbm": elems * 8 / ms / 1e6 / HBM}
+    ta = torch.empty(elems, dtype=torch.float64, device="cuda")
+    tb = torch.empty(elems, dtype=torch.float64, device="cuda")
+    ms = timeit(lambda: tb.copy_(ta))
+    res["torch copy_ yardstick (2*8 B/elem)"] = {"ms": ms, "GB/s": elems * 16 / ms / 1e6}
+    hbm[f"{n}x{n} fp64"] = res
+    del A, B, O, T, ta, tb
+out["hbm_kernels"] = hbm
+
+gemm = {}
+for n in (4096, 8192, 16384):
+    A = mb.MTUtils.randomBlockMatrix(None, n, n, 1, 1, seed=3, dtype=nat.MB_BF16).blocks[0][1]
+    B = mb.MTUtils.randomBlockMatrix(None, n, n, 1, 1, seed=4, dtype=nat.MB_BF16).blocks[0][1]
+    Cm = mb.SubMatrix.empty(n, n, nat.MB_F32)
+    C16 = mb.SubMatrix.empty(n, n, nat.MB_BF16)
+    iters = 10 if n <= 8192 else 4
+    ms32 = timeit(lambda: A.multiply(B, out=Cm), iters)
+    ms16 = timeit(lambda: A.multiply(B, out=C16), iters)
+    ta = A.buf.view(n, n)
+    tb = B.buf.view(n, n)
+    tc = torch.empty(n, n, dtype=torch.bfloat16, device="cuda")
+    msc = timeit(lambda: torch.matmul(tb, ta, out=tc), iters)        # column-major A*B == row-major B^T... same flops
+    fl = 2.0 * n ** 3
+    gemm[f"{n}^3"] = {"ours_f32out_ms": ms32, "ours_f32out_tflops": fl / ms32 / 1e9, "ours_bf16out_ms": ms16,
+                      "ours_bf16out_tflops": fl / ms16 / 1e9, "cublas_bf16_ms": msc, "cublas_bf16_tflops": fl / msc / 1e9,
+                      "frac_of_measured_bf16_peak": fl / ms32 / 1e9 / BF16}
+    del A, B, Cm, C16, ta, tb, tc
+out["bf16_gemm"] = gemm
+Path("gpurun_out").mkdir(exist_ok=True)
+Path("gpurun_out/kernels.json").write_text(json.dumps(out, indent=1))
+print(json.dumps(out, indent=1))
