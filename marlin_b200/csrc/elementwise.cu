@@ -34,42 +34,67 @@ __device__ __forceinline__ double apply_un(int op, double a, double alpha, doubl
 }
 
 // ---- flat (packed, same orientation) fast paths: 128-bit accesses, 4 independent loads in flight ----
+// Each CTA walks contiguous 16 KiB tiles (256 threads x 4 vectors of 16 B): every warp instruction touches 512
+// consecutive bytes and a tile stays inside a few DRAM pages; loads are non-allocating, stores streaming.
+__device__ __forceinline__ double2 ldg_stream(const double2* p) {
+    double2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void stg_stream(double2* p, double2 v) {
+    asm volatile("st.global.cs.v2.f64 [%0], {%1,%2};" ::"l"(p), "d"(v.x), "d"(v.y) : "memory");
+}
+
 template <int OP>
 __global__ void __launch_bounds__(EW_THREADS) binary_flat_kernel(const double2* __restrict__ a,
                                                                 const double2* __restrict__ b,
                                                                 double2* __restrict__ o, long long n2) {
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    for (; i + 3 * stride < n2; i += 4 * stride) {
-        double2 x[4], y[4];
+    constexpr int TILE = EW_THREADS * 4;
+    const long long num_tiles = (n2 + TILE - 1) / TILE;
+    for (long long t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const long long base = t * TILE + threadIdx.x;
+        if (base + 3 * EW_THREADS < n2) {
+            double2 x[4], y[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) { x[u] = __ldg(a + i + u * stride); y[u] = __ldg(b + i + u * stride); }
+            for (int u = 0; u < 4; ++u) { x[u] = ldg_stream(a + base + u * EW_THREADS); y[u] = ldg_stream(b + base + u * EW_THREADS); }
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
-            o[i + u * stride] = make_double2(apply_bin(OP, x[u].x, y[u].x), apply_bin(OP, x[u].y, y[u].y));
-    }
-    for (; i < n2; i += stride) {
-        const double2 x = __ldg(a + i), y = __ldg(b + i);
-        o[i] = make_double2(apply_bin(OP, x.x, y.x), apply_bin(OP, x.y, y.y));
+            for (int u = 0; u < 4; ++u)
+                stg_stream(o + base + u * EW_THREADS, make_double2(apply_bin(OP, x[u].x, y[u].x), apply_bin(OP, x[u].y, y[u].y)));
+        } else {
+            for (int u = 0; u < 4; ++u) {
+                const long long i = base + u * EW_THREADS;
+                if (i < n2) {
+                    const double2 x = a[i], y = b[i];
+                    o[i] = make_double2(apply_bin(OP, x.x, y.x), apply_bin(OP, x.y, y.y));
+                }
+            }
+        }
     }
 }
 
 template <int OP>
 __global__ void __launch_bounds__(EW_THREADS) unary_flat_kernel(const double2* __restrict__ a, double2* __restrict__ o,
                                                                long long n2, double alpha, double beta) {
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    for (; i + 3 * stride < n2; i += 4 * stride) {
-        double2 x[4];
+    constexpr int TILE = EW_THREADS * 4;
+    const long long num_tiles = (n2 + TILE - 1) / TILE;
+    for (long long t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const long long base = t * TILE + threadIdx.x;
+        if (base + 3 * EW_THREADS < n2) {
+            double2 x[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) x[u] = __ldg(a + i + u * stride);
+            for (int u = 0; u < 4; ++u) x[u] = ldg_stream(a + base + u * EW_THREADS);
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
-            o[i + u * stride] = make_double2(apply_un(OP, x[u].x, alpha, beta), apply_un(OP, x[u].y, alpha, beta));
-    }
-    for (; i < n2; i += stride) {
-        const double2 x = __ldg(a + i);
-        o[i] = make_double2(apply_un(OP, x.x, alpha, beta), apply_un(OP, x.y, alpha, beta));
+            for (int u = 0; u < 4; ++u)
+                stg_stream(o + base + u * EW_THREADS, make_double2(apply_un(OP, x[u].x, alpha, beta), apply_un(OP, x[u].y, alpha, beta)));
+        } else {
+            for (int u = 0; u < 4; ++u) {
+                const long long i = base + u * EW_THREADS;
+                if (i < n2) {
+                    const double2 x = a[i];
+                    o[i] = make_double2(apply_un(OP, x.x, alpha, beta), apply_un(OP, x.y, alpha, beta));
+                }
+            }
+        }
     }
 }
 
@@ -281,26 +306,41 @@ __device__ unsigned long long xs_jump(unsigned long long s, unsigned long long s
     }
     return s;
 }
-constexpr int FILL_CHUNK = 128;   // values per thread
+// Block = 256 threads, thread t generates FILL_CHUNK consecutive values of the stream into shared memory, then the
+// block writes its 8192 values with coalesced stores.  The jump is hierarchical: every thread applies the block's
+// base offset (shared bits of the step count) plus its own t*2*FILL_CHUNK steps.
+constexpr int FILL_CHUNK = 16;   // values per thread (256 x 17 x 8 B = 34 KiB of static smem)
 __global__ void __launch_bounds__(256) fill_uniform_kernel(double* out, long long rs, long long cs, int rows, int cols,
                                                           int row_major, unsigned long long state0, long long first,
                                                           double lo, double hi) {
+    __shared__ double stage[256][FILL_CHUNK + 1];
+    __shared__ unsigned long long base_state;
     const long long total = (long long)rows * cols;
-    const long long chunk = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    long long i = chunk * FILL_CHUNK;
-    if (i >= total) return;
-    const long long end = min(total, i + FILL_CHUNK);
-    unsigned long long s = xs_jump(state0, 2ull * (unsigned long long)(first + i));
+    const long long block_first = (long long)blockIdx.x * 256 * FILL_CHUNK;
+    if (block_first >= total) return;
+    if (threadIdx.x == 0) base_state = xs_jump(state0, 2ull * (unsigned long long)(first + block_first));
+    __syncthreads();
+    const long long i0 = block_first + (long long)threadIdx.x * FILL_CHUNK;
     const double span = __dsub_rn(hi, lo);
-    for (; i < end; ++i) {
-        s = xs_step(s);
-        const unsigned long long hi26 = s & ((1ull << 26) - 1);
-        s = xs_step(s);
-        const unsigned long long lo27 = s & ((1ull << 27) - 1);
-        const double u = (double)((hi26 << 27) + lo27) * 0x1.0p-53;
-        const double v = __dadd_rn(__dmul_rn(span, u), lo);
+    if (i0 < total) {
+        unsigned long long s = xs_jump(base_state, 2ull * (unsigned long long)threadIdx.x * FILL_CHUNK);
+        const int cnt = (int)min((long long)FILL_CHUNK, total - i0);
+        for (int v = 0; v < cnt; ++v) {
+            s = xs_step(s);
+            const unsigned long long hi26 = s & ((1ull << 26) - 1);
+            s = xs_step(s);
+            const unsigned long long lo27 = s & ((1ull << 27) - 1);
+            const double u = (double)((hi26 << 27) + lo27) * 0x1.0p-53;
+            stage[threadIdx.x][v] = __dadd_rn(__dmul_rn(span, u), lo);
+        }
+    }
+    __syncthreads();
+    const long long block_cnt = min((long long)256 * FILL_CHUNK, total - block_first);
+    for (long long e = threadIdx.x; e < block_cnt; e += 256) {
+        const long long i = block_first + e;
+        const double v = stage[e / FILL_CHUNK][e % FILL_CHUNK];
         long long r, c;
-        if (row_major) { r = i / cols; c = i % cols; } else { c = i / rows; r = i % rows; }
+        if (row_major) { r = i / cols; c = i - r * cols; } else { c = i / rows; r = i - c * rows; }
         out[r * rs + c * cs] = v;
     }
 }
@@ -322,7 +362,8 @@ cudaError_t ew_binary(int op, int rows, int cols, const double* a, long long ars
     const bool packed = ars == 1 && brs == 1 && ors == 1 && acs == rows && bcs == rows && ocs == rows;
     const bool aligned = ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) |
                            reinterpret_cast<uintptr_t>(o)) & 15) == 0;
-    if (packed && aligned && (total % 2 == 0)) {
+    const bool aliased = (static_cast<const void*>(a) == static_cast<const void*>(o)) || (static_cast<const void*>(b) == static_cast<const void*>(o));
+    if (packed && aligned && (total % 2 == 0) && !aliased) {
         const long long n2 = total / 2;
         const int grid = ew_grid((n2 + 3) / 4);
         const double2 *a2 = reinterpret_cast<const double2*>(a), *b2 = reinterpret_cast<const double2*>(b);
@@ -350,7 +391,7 @@ cudaError_t ew_unary(int op, int rows, int cols, const double* a, long long ars,
     const long long total = (long long)rows * cols;
     const bool packed = ars == 1 && ors == 1 && acs == rows && ocs == rows;
     const bool aligned = ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(o)) & 15) == 0;
-    if (packed && aligned && (total % 2 == 0)) {
+    if (packed && aligned && (total % 2 == 0) && static_cast<const void*>(a) != static_cast<const void*>(o)) {
         const long long n2 = total / 2;
         const int grid = ew_grid((n2 + 3) / 4);
         const double2* a2 = reinterpret_cast<const double2*>(a);
@@ -469,8 +510,8 @@ cudaError_t fill_uniform_f64(double* out, long long rs, long long cs, int rows, 
     cudaError_t e = fill_uniform_init_tables();
     if (e != cudaSuccess) return e;
     const long long total = (long long)rows * cols;
-    const long long chunks = (total + FILL_CHUNK - 1) / FILL_CHUNK;
-    const int blocks = (int)((chunks + 255) / 256);
+    const long long per_block = 256ll * FILL_CHUNK;
+    const int blocks = (int)((total + per_block - 1) / per_block);
     fill_uniform_kernel<<<blocks, 256, 0, st>>>(out, rs, cs, rows, cols, row_major, state0, first, lo, hi);
     return cudaGetLastError();
 }
