@@ -99,6 +99,16 @@ int32_t mb_dgemm_host(mb_ctx* ctx, char transa, char transb, int32_t m, int32_t 
                       double alpha, const double* a, int64_t a_offset, int32_t lda,
                       const double* b, int64_t b_offset, int32_t ldb,
                       double beta, double* c, int64_t c_offset, int32_t ldc);
+/* fp64 arithmetic mode of the block GEMM.  MB_FP64_NATIVE (default): the DMMA kernel, true IEEE fp64 FMAs.
+ * MB_FP64_INT8_SPLIT: large 'N','N' products run on the int8 tensor cores (tcgen05.mma.kind::i8) from `slices`
+ * 7-bit digit planes per operand (Ozaki split; 2..8, 7 recommended): error <= ~K * 2^(-7*slices+2) relative to
+ * rowmax(A) * colmax(B), i.e. well inside 1e-10 for well-scaled data but NOT an element-wise fp64 guarantee, hence
+ * opt-in.  Products the split does not cover (transposed views, small blocks, K too large for exact int32
+ * accumulation) silently use the native kernel. */
+#define MB_FP64_NATIVE      0
+#define MB_FP64_INT8_SPLIT  1
+int32_t mb_set_fp64_mode(mb_ctx* ctx, int32_t mode, int32_t slices);
+
 /* Force the generic (non-TMA, CUDA-core DFMA) kernel: test hook + path for odd ld / unaligned views. */
 int32_t mb_dgemm_device_generic(mb_ctx* ctx, char transa, char transb, int32_t m, int32_t n, int32_t k,
                                 double alpha, const double* A, int32_t lda, const double* B, int32_t ldb,

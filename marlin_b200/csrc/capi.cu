@@ -5,6 +5,7 @@
 #include "elementwise.h"
 #include "gemm_f64.h"
 #include "gemm_bf16.h"
+#include "gemm_ozaki.h"
 
 #include <cuda_runtime.h>
 #include <cstdarg>
@@ -27,6 +28,11 @@ struct mb_ctx {
     cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
     void* workspace = nullptr;
     size_t workspace_bytes = 0;
+    // fp64 mode (mb_set_fp64_mode) and the digit-plane workspace of the int8-split path
+    int fp64_mode = MB_FP64_NATIVE;
+    int fp64_slices = 7;
+    void* ozaki_ws = nullptr;
+    size_t ozaki_ws_bytes = 0;
 };
 
 struct mb_block {
@@ -222,6 +228,7 @@ int32_t mb_shutdown(mb_ctx* ctx) {
     if (ctx->h2d_stream) cudaStreamDestroy(ctx->h2d_stream);
     if (ctx->d2h_stream) cudaStreamDestroy(ctx->d2h_stream);
     if (ctx->workspace) cudaFree(ctx->workspace);
+    if (ctx->ozaki_ws) cudaFree(ctx->ozaki_ws);
     delete ctx;
     return MB_OK;
 }
@@ -415,8 +422,32 @@ static int32_t dgemm_device_impl(mb_ctx* ctx, char transa, char transb, int32_t 
     if (m == 0 || n == 0) return MB_OK;
     if (!C || (k > 0 && alpha != 0.0 && (!A || !B))) return fail(MB_ERR_INVALID_ARG, "dgemm: null pointer");
     int launches = 0;
+    if (ctx->fp64_mode == MB_FP64_INT8_SPLIT && !force_generic && !ta && !tb && alpha == 1.0 && (beta == 0.0 || beta == 1.0) &&
+        m >= 256 && n >= 256 && k >= 256 && mb::ozaki_supported(m, n, k, ctx->fp64_slices)) {
+        const size_t need = mb::ozaki_workspace_bytes(m, n, k, ctx->fp64_slices);
+        if (need > ctx->ozaki_ws_bytes) {
+            if (ctx->ozaki_ws) { MB_CUDA(cudaStreamSynchronize(ctx->stream)); cudaFree(ctx->ozaki_ws); ctx->ozaki_ws = nullptr; ctx->ozaki_ws_bytes = 0; }
+            MB_CUDA(cudaMalloc(&ctx->ozaki_ws, need));
+            ctx->ozaki_ws_bytes = need;
+        }
+        cudaError_t e = mb::gemm_f64_ozaki(m, n, k, A, lda, B, ldb, C, ldc, beta == 1.0, ctx->fp64_slices, ctx->ozaki_ws,
+                                           ctx->num_sms, ctx->stream, &launches);
+        if (e == cudaSuccess) { ctx->launches += launches; return MB_OK; }
+        if (e != cudaErrorNotSupported) return cuda_fail(e, "gemm_f64_ozaki");
+        cudaGetLastError();
+        launches = 0;
+    }
     MB_CUDA(mb::gemm_f64(ta, tb, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, ctx->num_sms, ctx->stream, force_generic, &launches));
     ctx->launches += launches;
+    return MB_OK;
+}
+
+int32_t mb_set_fp64_mode(mb_ctx* ctx, int32_t mode, int32_t slices) {
+    if (!ctx) return fail(MB_ERR_INVALID_ARG, "null context");
+    if (mode != MB_FP64_NATIVE && mode != MB_FP64_INT8_SPLIT) return fail(MB_ERR_INVALID_ARG, "mb_set_fp64_mode: unknown mode %d", mode);
+    if (mode == MB_FP64_INT8_SPLIT && (slices < 2 || slices > 8)) return fail(MB_ERR_INVALID_ARG, "mb_set_fp64_mode: slices must be in 2..8");
+    ctx->fp64_mode = mode;
+    if (mode == MB_FP64_INT8_SPLIT) ctx->fp64_slices = slices;
     return MB_OK;
 }
 
@@ -527,7 +558,7 @@ int32_t mb_matmul_blocked_subset(mb_ctx* ctx, mb_block* const* A_tiles, mb_block
         }
     }
     // ---- grouped single launch when every operand is an fp64 column-major ('N') block ----
-    bool groupable = num_c > 0;
+    bool groupable = num_c > 0 && ctx->fp64_mode == MB_FP64_NATIVE;
     std::vector<const double*> Ap(m * k, nullptr), Bp(k * n, nullptr);
     std::vector<double*> Cp(m * n, nullptr);
     std::vector<long long> lda(m * k, 2), ldb(k * n, 2), ldc(m * n, 2);
