@@ -310,20 +310,35 @@ __device__ unsigned long long xs_jump(unsigned long long s, unsigned long long s
 // block writes its 8192 values with coalesced stores.  The jump is hierarchical: every thread applies the block's
 // base offset (shared bits of the step count) plus its own t*2*FILL_CHUNK steps.
 constexpr int FILL_CHUNK = 16;   // values per thread (256 x 17 x 8 B = 34 KiB of static smem)
+constexpr int FILL_LO = 5, FILL_LEVELS = 8;   // thread offset = tid * 2 * FILL_CHUNK steps = tid << 5: bits 5..12
 __global__ void __launch_bounds__(256) fill_uniform_kernel(double* out, long long rs, long long cs, int rows, int cols,
                                                           int row_major, unsigned long long state0, long long first,
                                                           double lo, double hi) {
     __shared__ double stage[256][FILL_CHUNK + 1];
+    __shared__ unsigned long long jump_s[FILL_LEVELS][64];   // lane-divergent lookups: shared memory, not __constant__
     __shared__ unsigned long long base_state;
     const long long total = (long long)rows * cols;
     const long long block_first = (long long)blockIdx.x * 256 * FILL_CHUNK;
     if (block_first >= total) return;
+    for (int e = threadIdx.x; e < FILL_LEVELS * 64; e += 256) jump_s[e >> 6][e & 63] = c_jump[FILL_LO + (e >> 6)][e & 63];
     if (threadIdx.x == 0) base_state = xs_jump(state0, 2ull * (unsigned long long)(first + block_first));
     __syncthreads();
     const long long i0 = block_first + (long long)threadIdx.x * FILL_CHUNK;
     const double span = __dsub_rn(hi, lo);
     if (i0 < total) {
-        unsigned long long s = xs_jump(base_state, 2ull * (unsigned long long)threadIdx.x * FILL_CHUNK);
+        unsigned long long s = base_state;
+        unsigned steps = threadIdx.x;             // in units of 2^FILL_LO xorshift steps
+#pragma unroll 1
+        for (int j = 0; j < FILL_LEVELS && steps; ++j, steps >>= 1) {
+            if (steps & 1u) {
+                unsigned long long t = 0, x = s;
+                while (x) {
+                    t ^= jump_s[j][__ffsll((long long)x) - 1];
+                    x &= x - 1;
+                }
+                s = t;
+            }
+        }
         const int cnt = (int)min((long long)FILL_CHUNK, total - i0);
         for (int v = 0; v < cnt; ++v) {
             s = xs_step(s);
