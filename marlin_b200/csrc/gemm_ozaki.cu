@@ -17,6 +17,7 @@
 // and an fp64 read-modify-write epilogue.
 #include "gemm_ozaki.h"
 #include "ptx.cuh"
+#include <cstdlib>
 
 namespace mb {
 
@@ -263,6 +264,231 @@ gemm_ozaki_i8_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
     }
 }
 
+// -------------------------------------------------------------------------------------------
+// 2-CTA variant (cta_group::2): a cluster of two CTAs on one TPC computes a 256 x 256 tile.  Each CTA stages its own
+// 128 rows of the A plane and HALF of the B plane (128 of the 256 columns); one tcgen05.mma.cta_group::2 issued by the
+// leader CTA drives both SMs' tensor cores, reading B from both CTAs' shared memory.  Per SM and k-slab that is
+// 32 KiB from L2 instead of 48 KiB for the same 128 x 256 x 128 MACs — the int8 path is L2 -> SM bandwidth bound,
+// so this is worth ~1.5x.  Barriers: `full` and `tmem_empty` live in the leader CTA (remote arrives / TMA
+// complete_tx from the peer), `empty` and `tmem_full` are multicast by tcgen05.commit to both CTAs.
+// -------------------------------------------------------------------------------------------
+constexpr int STAGE2_BYTES = 2 * A_BYTES;          // A 128x128 + B half 128x128 = 32 KiB
+constexpr int NUM_STAGES2 = 6;                     // 192 KiB
+constexpr int SMEM2_BYTES = NUM_STAGES2 * STAGE2_BYTES + 1024 + 256;
+constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;        // clears the CTA-rank bit of a shared::cluster address (-> leader CTA)
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_3d_2sm(uint32_t dst_smem, const CUtensorMap* map, uint32_t leader_bar, int32_t c0,
+                                                int32_t c1, int32_t c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(dst_smem), "l"(reinterpret_cast<uint64_t>(map)), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+// arrive (+ expect_tx) on the barrier at the same offset in CTA `cta` of the cluster
+__device__ __forceinline__ void mbar_arrive_expect_tx_remote(uint32_t bar, uint32_t cta, uint32_t bytes) {
+    asm volatile(
+        "{\n\t.reg .b32 ra;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+        "mbarrier.arrive.expect_tx.shared::cluster.b64 _, [ra], %2;\n\t}"
+        ::"r"(bar), "r"(cta), "r"(bytes)
+        : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t cta) {
+    asm volatile(
+        "{\n\t.reg .b32 ra;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+        "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
+        ::"r"(bar), "r"(cta)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish_2sm() {
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"((uint16_t)3)
+                 : "memory");
+}
+__device__ __forceinline__ void umma_i8_2sm(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+        : "memory");
+}
+// s8 x s8 -> s32, A MN-major, B K-major, M = 256 (two CTAs), N = 256
+__host__ __device__ constexpr uint32_t instr_desc_i8_2sm() {
+    return (2u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (0u << 16) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+gemm_ozaki_i8_2cta_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const Params p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bar_base = smem_base + NUM_STAGES2 * STAGE2_BYTES;
+    const uint32_t bar_full = bar_base;                        // used in the leader CTA only
+    const uint32_t bar_empty = bar_full + 8 * NUM_STAGES2;     // per CTA
+    const uint32_t bar_tfull = bar_empty + 8 * NUM_STAGES2;    // per CTA
+    const uint32_t bar_tempty = bar_tfull + 8 * NUM_ACC;       // used in the leader CTA only
+    const uint32_t tmem_slot = bar_tempty + 8 * NUM_ACC;
+    const uint32_t* tmem_slot_ptr = reinterpret_cast<const uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int cluster_id = blockIdx.x >> 1;
+    const int num_clusters = gridDim.x >> 1;
+    const int num_tiles = p.tiles_m * p.tiles_n;               // 256 x 256 cluster tiles
+    const int num_kb = (p.K + BK - 1) / BK;
+    const int s = p.s;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < NUM_STAGES2; ++i) { mbar_init(bar_full + 8 * i, 2); mbar_init(bar_empty + 8 * i, 1); }
+        for (int a = 0; a < NUM_ACC; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, 8); }
+        fence_barrier_init();
+        tma_prefetch_desc(&mapA);
+        tma_prefetch_desc(&mapB);
+    }
+    if (warp == 1) {
+        tmem_alloc_2sm(tmem_slot, NUM_ACC * BN);
+        tmem_relinquish_2sm();
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int t = cluster_id; t < num_tiles; t += num_clusters) {
+                int tm, tn;
+                tile_coords(t, p.tiles_m, p.tiles_n, tm, tn);
+                const int m0 = tm * 256 + 128 * (int)rank, n0 = tn * 256 + 128 * (int)rank;
+                for (int d = s + 1; d >= 2; --d) {
+                    const int t_lo = max(1, d - s), t_hi = min(s, d - 1);
+                    for (int ta = t_lo; ta <= t_hi; ++ta) {
+                        const int ub = d - ta;
+                        for (int kb = 0; kb < num_kb; ++kb) {
+                            mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+                            const uint32_t full_local = bar_full + 8 * stage;
+                            const uint32_t sA = smem_base + stage * STAGE2_BYTES;
+                            mbar_arrive_expect_tx_remote(full_local, 0, STAGE2_BYTES);
+                            tma_load_3d_2sm(sA, &mapA, full_local & PEER_MASK, m0, kb * BK, ta - 1);
+                            tma_load_3d_2sm(sA + A_BYTES, &mapB, full_local & PEER_MASK, kb * BK, n0, ub - 1);
+                            if (++stage == NUM_STAGES2) { stage = 0; phase ^= 1; }
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (rank == 0 && lane == 0) {
+            constexpr uint32_t idesc = instr_desc_i8_2sm();
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int t = cluster_id; t < num_tiles; t += num_clusters) {
+                for (int d = s + 1; d >= 2; --d) {
+                    mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + acc * BN;
+                    const int npairs = min(s, d - 1) - max(1, d - s) + 1;
+                    uint32_t first = 1;
+                    for (int pr = 0; pr < npairs; ++pr) {
+                        for (int kb = 0; kb < num_kb; ++kb) {
+                            mbar_wait(bar_full + 8 * stage, phase);
+                            tc_fence_after();
+                            const uint32_t sA = smem_base + stage * STAGE2_BYTES;
+                            const uint32_t sB = sA + A_BYTES;
+#pragma unroll
+                            for (int k = 0; k < BK / 32; ++k) {
+                                const uint64_t adesc = smem_desc(sA + k * 4096, 0, 1024);
+                                const uint64_t bdesc = smem_desc(sB + k * 32, 0, 1024);
+                                umma_i8_2sm(d_tmem, adesc, bdesc, idesc, first ? 0u : 1u);
+                                first = 0;
+                            }
+                            umma_commit_2sm(bar_empty + 8 * stage);      // frees this stage in BOTH CTAs
+                            if (++stage == NUM_STAGES2) { stage = 0; phase ^= 1; }
+                        }
+                    }
+                    umma_commit_2sm(bar_tfull + 8 * acc);                 // accumulator ready in BOTH CTAs
+                    if (++acc == NUM_ACC) { acc = 0; acc_phase ^= 1; }
+                }
+            }
+        }
+    } else {
+        const int quarter = warp & 3;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        const int P2 = 2 * (7 * s - 1);
+        for (int t = cluster_id; t < num_tiles; t += num_clusters) {
+            int tm, tn;
+            tile_coords(t, p.tiles_m, p.tiles_n, tm, tn);
+            const int m = tm * 256 + 128 * (int)rank + quarter * 32 + lane;
+            const int n0 = tn * 256;
+            const bool m_ok = m < p.M;
+            const int ea = m_ok ? __ldg(p.eA + m) : 0;
+            double* crow = p.C + m;
+            for (int d = s + 1; d >= 2; --d) {
+                const bool init = (d == s + 1) && !p.accumulate;
+                const int ex_m = ea - P2 + 7 * (2 * s - d);
+                mbar_wait(bar_tfull + 8 * acc, acc_phase);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN;
+#pragma unroll 1
+                for (int c = 0; c < BN / 32; ++c) {
+                    uint32_t v[32];
+                    tmem_ld32(taddr + c * 32, v);
+                    tmem_ld_wait();
+                    if (c == BN / 32 - 1) {
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive_remote(bar_tempty + 8 * acc, 0);   // leader's barrier: 4 warps x 2 CTAs
+                    }
+                    if (m_ok) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const int n = n0 + c * 32 + j;
+                            if (n < p.N) {
+                                const double term = (double)(int)v[j] * pow2_scale(ex_m + __ldg(p.eB + n));
+                                double* dst = crow + (long long)n * p.ldc;
+                                *dst = init ? term : (*dst + term);
+                            }
+                        }
+                    }
+                }
+                if (++acc == NUM_ACC) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    }
+
+    tc_fence_before();
+    cluster_sync_all();          // nobody leaves (or frees TMEM) while the pair may still touch its smem / barriers
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc_2sm(tmem_base, NUM_ACC * BN);
+    }
+}
+
 // ------------------------------------------------------------------------------------------- operand splitting
 __global__ void ozaki_rowmax_kernel(const double* __restrict__ A, long long lda, int M, int K, int kchunk,
                                     unsigned long long* __restrict__ rowmax_bits) {
@@ -414,6 +640,27 @@ cudaError_t gemm_f64_ozaki(int M, int N, int K, const double* A, long long lda, 
     p.tiles_m = (M + BM - 1) / BM;
     p.tiles_n = (N + BN - 1) / BN;
     p.accumulate = accumulate ? 1 : 0;
+    static int use_2cta = -1;
+    if (use_2cta < 0) {
+        const char* env = getenv("MARLIN_B200_TC_2CTA");
+        use_2cta = (env && env[0] == '0') ? 0 : 1;
+    }
+    if (use_2cta && M > 128 && N > 128) {
+        // cluster pairs: 256 x 256 tiles, B split across the two CTAs (box 128 k x 128 n)
+        if (!make_map_i8_3d(&mB, B8, K, N, s, ldB, planeB, 128, 128)) return cudaErrorNotSupported;
+        p.tiles_m = (M + 255) / 256;
+        p.tiles_n = (N + 255) / 256;
+        static bool attr2_done = false;
+        if (!attr2_done) {
+            e = cudaFuncSetAttribute(gemm_ozaki_i8_2cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES);
+            if (e != cudaSuccess) return e;
+            attr2_done = true;
+        }
+        const int clusters = min(p.tiles_m * p.tiles_n, num_sms / 2);
+        gemm_ozaki_i8_2cta_kernel<<<2 * clusters, NUM_THREADS, SMEM2_BYTES, stream>>>(mA, mB, p);
+        if (launches) ++*launches;
+        return cudaGetLastError();
+    }
     static bool attr_done = false;
     if (!attr_done) {
         e = cudaFuncSetAttribute(gemm_ozaki_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
