@@ -114,6 +114,28 @@ __device__ __forceinline__ double pow2_scale(int ex) {
     return ldexp(1.0, ex);
 }
 
+// One 32-column chunk of one digit group: C[m][n0..n0+31] (+)= acc * 2^(ex_m + eB[n]).  All 32 old values of C are
+// loaded before any store so the read-modify-write costs ONE memory latency per chunk instead of 32 dependent ones.
+__device__ __forceinline__ void fold_group_chunk(const uint32_t (&v)[32], double* crow, long long ldc, int n_first, int N,
+                                                 const int* __restrict__ eB, int ex_m, bool init) {
+    double old[32];
+    if (!init) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            const int n = n_first + j;
+            old[j] = (n < N) ? __ldcg(crow + (long long)n * ldc) : 0.0;
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        const int n = n_first + j;
+        if (n < N) {
+            const double term = (double)(int)v[j] * pow2_scale(ex_m + __ldg(eB + n));
+            crow[(long long)n * ldc] = init ? term : (old[j] + term);
+        }
+    }
+}
+
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_ozaki_i8_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const Params p) {
     extern __shared__ uint8_t smem_raw[];
@@ -239,17 +261,7 @@ gemm_ozaki_i8_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
                         __syncwarp();
                         if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
                     }
-                    if (m_ok) {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            const int n = n0 + c * 32 + j;
-                            if (n < p.N) {
-                                const double term = (double)(int)v[j] * pow2_scale(ex_m + __ldg(p.eB + n));
-                                double* dst = crow + (long long)n * p.ldc;
-                                *dst = init ? term : (*dst + term);
-                            }
-                        }
-                    }
+                    if (m_ok) fold_group_chunk(v, crow, p.ldc, n0 + c * 32, p.N, p.eB, ex_m, init);
                 }
                 if (++acc == NUM_ACC) { acc = 0; acc_phase ^= 1; }
             }
@@ -464,17 +476,7 @@ gemm_ozaki_i8_2cta_kernel(const __grid_constant__ CUtensorMap mapA, const __grid
                         __syncwarp();
                         if (lane == 0) mbar_arrive_remote(bar_tempty + 8 * acc, 0);   // leader's barrier: 4 warps x 2 CTAs
                     }
-                    if (m_ok) {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            const int n = n0 + c * 32 + j;
-                            if (n < p.N) {
-                                const double term = (double)(int)v[j] * pow2_scale(ex_m + __ldg(p.eB + n));
-                                double* dst = crow + (long long)n * p.ldc;
-                                *dst = init ? term : (*dst + term);
-                            }
-                        }
-                    }
+                    if (m_ok) fold_group_chunk(v, crow, p.ldc, n0 + c * 32, p.N, p.eB, ex_m, init);
                 }
                 if (++acc == NUM_ACC) { acc = 0; acc_phase ^= 1; }
             }
