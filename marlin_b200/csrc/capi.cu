@@ -31,6 +31,7 @@ struct mb_ctx {
     // fp64 mode (mb_set_fp64_mode) and the digit-plane workspace of the int8-split path
     int fp64_mode = MB_FP64_NATIVE;
     int fp64_slices = 7;
+    int fp64_bits = 7;
     void* ozaki_ws = nullptr;
     size_t ozaki_ws_bytes = 0;
 };
@@ -422,15 +423,15 @@ static int32_t dgemm_device_impl(mb_ctx* ctx, char transa, char transb, int32_t 
     if (m == 0 || n == 0) return MB_OK;
     if (!C || (k > 0 && alpha != 0.0 && (!A || !B))) return fail(MB_ERR_INVALID_ARG, "dgemm: null pointer");
     int launches = 0;
-    if (ctx->fp64_mode == MB_FP64_INT8_SPLIT && !force_generic && !ta && !tb && alpha == 1.0 && (beta == 0.0 || beta == 1.0) &&
-        m >= 256 && n >= 256 && k >= 256 && mb::ozaki_supported(m, n, k, ctx->fp64_slices)) {
+    if (ctx->fp64_mode != MB_FP64_NATIVE && !force_generic && !ta && !tb && alpha == 1.0 && (beta == 0.0 || beta == 1.0) &&
+        m >= 256 && n >= 256 && k >= 256 && mb::ozaki_supported(m, n, k, ctx->fp64_slices, ctx->fp64_bits)) {
         const size_t need = mb::ozaki_workspace_bytes(m, n, k, ctx->fp64_slices);
         if (need > ctx->ozaki_ws_bytes) {
             if (ctx->ozaki_ws) { MB_CUDA(cudaStreamSynchronize(ctx->stream)); cudaFree(ctx->ozaki_ws); ctx->ozaki_ws = nullptr; ctx->ozaki_ws_bytes = 0; }
             MB_CUDA(cudaMalloc(&ctx->ozaki_ws, need));
             ctx->ozaki_ws_bytes = need;
         }
-        cudaError_t e = mb::gemm_f64_ozaki(m, n, k, A, lda, B, ldb, C, ldc, beta == 1.0, ctx->fp64_slices, ctx->ozaki_ws,
+        cudaError_t e = mb::gemm_f64_ozaki(m, n, k, A, lda, B, ldb, C, ldc, beta == 1.0, ctx->fp64_slices, ctx->fp64_bits, ctx->ozaki_ws,
                                            ctx->num_sms, ctx->stream, &launches);
         if (e == cudaSuccess) { ctx->launches += launches; return MB_OK; }
         if (e != cudaErrorNotSupported) return cuda_fail(e, "gemm_f64_ozaki");
@@ -444,10 +445,11 @@ static int32_t dgemm_device_impl(mb_ctx* ctx, char transa, char transb, int32_t 
 
 int32_t mb_set_fp64_mode(mb_ctx* ctx, int32_t mode, int32_t slices) {
     if (!ctx) return fail(MB_ERR_INVALID_ARG, "null context");
-    if (mode != MB_FP64_NATIVE && mode != MB_FP64_INT8_SPLIT) return fail(MB_ERR_INVALID_ARG, "mb_set_fp64_mode: unknown mode %d", mode);
-    if (mode == MB_FP64_INT8_SPLIT && (slices < 2 || slices > 8)) return fail(MB_ERR_INVALID_ARG, "mb_set_fp64_mode: slices must be in 2..8");
+    if (mode != MB_FP64_NATIVE && mode != MB_FP64_INT8_SPLIT && mode != MB_FP64_INT8_SPLIT8)
+        return fail(MB_ERR_INVALID_ARG, "mb_set_fp64_mode: unknown mode %d", mode);
+    if (mode != MB_FP64_NATIVE && (slices < 2 || slices > 8)) return fail(MB_ERR_INVALID_ARG, "mb_set_fp64_mode: slices must be in 2..8");
     ctx->fp64_mode = mode;
-    if (mode == MB_FP64_INT8_SPLIT) ctx->fp64_slices = slices;
+    if (mode != MB_FP64_NATIVE) { ctx->fp64_slices = slices; ctx->fp64_bits = (mode == MB_FP64_INT8_SPLIT8) ? 8 : 7; }
     return MB_OK;
 }
 

@@ -35,6 +35,8 @@ constexpr int BAND = 16;
 
 struct Params {
     int M, N, K, s;
+    int bits;          // digit width: 7 (|digit| <= 64) or 8 (|digit| <= 128, top digit <= 64)
+    int P;             // fractional bits of the scaled operands: bits*s - (bits == 8 ? 2 : 1)
     double* C;
     long long ldc;
     const int* eA;
@@ -236,7 +238,7 @@ gemm_ozaki_i8_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
         const int quarter = warp & 3;
         int acc = 0;
         uint32_t acc_phase = 0;
-        const int P2 = 2 * (7 * s - 1);
+        const int P2 = 2 * p.P;
         for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
             int tm, tn;
             tile_coords(t, p.tiles_m, p.tiles_n, tm, tn);
@@ -247,7 +249,7 @@ gemm_ozaki_i8_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
             double* crow = p.C + m;
             for (int d = s + 1; d >= 2; --d) {
                 const bool init = (d == s + 1) && !p.accumulate;
-                const int ex_m = ea - P2 + 7 * (2 * s - d);
+                const int ex_m = ea - P2 + p.bits * (2 * s - d);
                 mbar_wait(bar_tfull + 8 * acc, acc_phase);
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN;
@@ -451,7 +453,7 @@ gemm_ozaki_i8_2cta_kernel(const __grid_constant__ CUtensorMap mapA, const __grid
         const int quarter = warp & 3;
         int acc = 0;
         uint32_t acc_phase = 0;
-        const int P2 = 2 * (7 * s - 1);
+        const int P2 = 2 * p.P;
         for (int t = cluster_id; t < num_tiles; t += num_clusters) {
             int tm, tn;
             tile_coords(t, p.tiles_m, p.tiles_n, tm, tn);
@@ -462,7 +464,7 @@ gemm_ozaki_i8_2cta_kernel(const __grid_constant__ CUtensorMap mapA, const __grid
             double* crow = p.C + m;
             for (int d = s + 1; d >= 2; --d) {
                 const bool init = (d == s + 1) && !p.accumulate;
-                const int ex_m = ea - P2 + 7 * (2 * s - d);
+                const int ex_m = ea - P2 + p.bits * (2 * s - d);
                 mbar_wait(bar_tfull + 8 * acc, acc_phase);
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN;
@@ -510,19 +512,19 @@ __device__ __forceinline__ int scale_exponent(double r) {
 }
 
 // digits of X = rint(a * 2^(P - e)), most significant first: out[t] for t = 0..s-1, each in [-64, 64]
-__device__ __forceinline__ void split_digits(double a, int e, int s, signed char* digs) {
-    const int P = 7 * s - 1;
+__device__ __forceinline__ void split_digits(double a, int e, int s, int bits, int P, signed char* digs) {
     long long X = __double2ll_rn(ldexp(a, P - e));
+    const long long half = 1ll << (bits - 1), mask = (1ll << bits) - 1;
     for (int t = s - 1; t >= 1; --t) {
-        const long long dgt = ((X + 64) & 127) - 64;
+        const long long dgt = ((X + half) & mask) - half;
         digs[t] = (signed char)dgt;
-        X = (X - dgt) >> 7;
+        X = (X - dgt) >> bits;
     }
-    digs[0] = (signed char)X;
+    digs[0] = (signed char)X;          // |X| <= 64 by the choice of P
 }
 
 // A (M x K, column-major) -> planes A8[t][k * ld8 + m]
-__global__ void ozaki_split_a_kernel(const double* __restrict__ A, long long lda, int M, int K, int s,
+__global__ void ozaki_split_a_kernel(const double* __restrict__ A, long long lda, int M, int K, int s, int bits, int P,
                                      const unsigned long long* __restrict__ rowmax_bits, signed char* __restrict__ A8,
                                      long long ld8, long long plane, int* __restrict__ eA) {
     const int m = blockIdx.x * blockDim.x + threadIdx.x;
@@ -533,13 +535,14 @@ __global__ void ozaki_split_a_kernel(const double* __restrict__ A, long long lda
     const int k0 = blockIdx.y * kchunk, k1 = min(K, k0 + kchunk);
     signed char digs[8];
     for (int k = k0; k < k1; ++k) {
-        split_digits(A[m + (long long)k * lda], e, s, digs);
+        split_digits(A[m + (long long)k * lda], e, s, bits, P, digs);
         for (int t = 0; t < s; ++t) A8[t * plane + (long long)k * ld8 + m] = digs[t];
     }
 }
 
 // B (K x N, column-major): one block per column -> planes B8[u][j * ld8 + k] (k contiguous)
 __global__ void __launch_bounds__(256) ozaki_split_b_kernel(const double* __restrict__ B, long long ldb, int K, int N, int s,
+                                                           int bits, int P,
                                                            signed char* __restrict__ B8, long long ld8, long long plane,
                                                            int* __restrict__ eB) {
     __shared__ double red[8];
@@ -558,7 +561,7 @@ __global__ void __launch_bounds__(256) ozaki_split_b_kernel(const double* __rest
     if (threadIdx.x == 0) eB[j] = e;
     signed char digs[8];
     for (int k = threadIdx.x; k < K; k += 256) {
-        split_digits(col[k], e, s, digs);
+        split_digits(col[k], e, s, bits, P, digs);
         for (int t = 0; t < s; ++t) B8[t * plane + (long long)j * ld8 + k] = digs[t];
     }
 }
@@ -601,15 +604,17 @@ size_t ozaki_workspace_bytes(int M, int N, int K, int s) {
            round_up((size_t)N * 4, 256);
 }
 
-bool ozaki_supported(int M, int N, int K, int s) {
-    // int32 accumulation of up to s pairs of K products of magnitude <= 64*64 must stay below 2^31
-    return s >= 2 && s <= 8 && M > 0 && N > 0 && K > 0 && (long long)K * s * 4096 < (1ll << 31) && get_encode_fn() != nullptr;
+bool ozaki_supported(int M, int N, int K, int s, int bits) {
+    // int32 accumulation of up to s pairs of K products of magnitude <= 2^(2*(bits-1)) must stay below 2^31
+    return s >= 2 && s <= 8 && (bits == 7 || bits == 8) && M > 0 && N > 0 && K > 0 &&
+           (long long)K * s * (1ll << (2 * (bits - 1))) < (1ll << 31) && get_encode_fn() != nullptr;
 }
 
 cudaError_t gemm_f64_ozaki(int M, int N, int K, const double* A, long long lda, const double* B, long long ldb, double* C,
-                           long long ldc, bool accumulate, int s, void* workspace, int num_sms, cudaStream_t stream,
+                           long long ldc, bool accumulate, int s, int bits, void* workspace, int num_sms, cudaStream_t stream,
                            int* launches) {
-    if (!ozaki_supported(M, N, K, s)) return cudaErrorNotSupported;
+    if (!ozaki_supported(M, N, K, s, bits)) return cudaErrorNotSupported;
+    const int P = bits * s - (bits == 8 ? 2 : 1);
     const size_t ldA = round_up((size_t)M, 16), ldB = round_up((size_t)K, 16);
     const size_t planeA = ldA * K, planeB = ldB * N;
     char* w = static_cast<char*>(workspace);
@@ -629,8 +634,8 @@ cudaError_t gemm_f64_ozaki(int M, int N, int K, const double* A, long long lda, 
     const int kchunk = (K + ksplit - 1) / ksplit;
     dim3 grid_a((M + 127) / 128, ksplit);
     ozaki_rowmax_kernel<<<grid_a, 128, 0, stream>>>(A, lda, M, K, kchunk, rowmax);
-    ozaki_split_a_kernel<<<grid_a, 128, 0, stream>>>(A, lda, M, K, s, rowmax, A8, (long long)ldA, (long long)planeA, eA);
-    ozaki_split_b_kernel<<<N, 256, 0, stream>>>(B, ldb, K, N, s, B8, (long long)ldB, (long long)planeB, eB);
+    ozaki_split_a_kernel<<<grid_a, 128, 0, stream>>>(A, lda, M, K, s, bits, P, rowmax, A8, (long long)ldA, (long long)planeA, eA);
+    ozaki_split_b_kernel<<<N, 256, 0, stream>>>(B, ldb, K, N, s, bits, P, B8, (long long)ldB, (long long)planeB, eB);
     if (launches) *launches += 3;
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
 
@@ -638,14 +643,14 @@ cudaError_t gemm_f64_ozaki(int M, int N, int K, const double* A, long long lda, 
     if (!make_map_i8_3d(&mA, A8, M, K, s, ldA, planeA, 128, 128)) return cudaErrorNotSupported;
     if (!make_map_i8_3d(&mB, B8, K, N, s, ldB, planeB, 128, 256)) return cudaErrorNotSupported;
     Params p;
-    p.M = M; p.N = N; p.K = K; p.s = s; p.C = C; p.ldc = ldc; p.eA = eA; p.eB = eB;
+    p.M = M; p.N = N; p.K = K; p.s = s; p.bits = bits; p.P = P; p.C = C; p.ldc = ldc; p.eA = eA; p.eB = eB;
     p.tiles_m = (M + BM - 1) / BM;
     p.tiles_n = (N + BN - 1) / BN;
     p.accumulate = accumulate ? 1 : 0;
     static int use_2cta = -1;
     if (use_2cta < 0) {
         const char* env = getenv("MARLIN_B200_TC_2CTA");
-        use_2cta = (env && env[0] == '0') ? 0 : 1;
+        use_2cta = (env && env[0] == '1') ? 1 : 0;     // measured: no gain (not L2-bound), so opt-in
     }
     if (use_2cta && M > 128 && N > 128) {
         // cluster pairs: 256 x 256 tiles, B split across the two CTAs (box 128 k x 128 n)

@@ -42,15 +42,16 @@ for n in sizes:
     t_nat = timeit(lambda: A.multiply(B, out=Cn), iters)
     res = {"native_ms": t_nat, "native_tflops": fl / t_nat / 1e9}
     ref = Cn.buf[: n * n]
-    for s in (6, 7, 8):
-        nat.check(lib.mb_set_fp64_mode(ctx, 1, s))
+    for mode, s in ((1, 6), (1, 7), (2, 5), (2, 6), (2, 4)):
+        nat.check(lib.mb_set_fp64_mode(ctx, mode, s))
         t = timeit(lambda: A.multiply(B, out=Co), iters)
         got = Co.buf[: n * n]
         rel = ((got - ref).abs() / ref.abs()).max().item()      # U[0,1) inputs: ref = (|A||B|)_ij
-        res[f"split{s}_ms"] = t
-        res[f"split{s}_tflops_equiv"] = fl / t / 1e9
-        res[f"split{s}_int8_tops"] = fl * (s * (s + 1) // 2) / t / 1e9
-        res[f"split{s}_max_scaled_err_vs_native"] = rel
+        tag = f"b{7 if mode == 1 else 8}s{s}"
+        res[f"{tag}_ms"] = round(t, 3)
+        res[f"{tag}_tflops_equiv"] = round(fl / t / 1e9, 2)
+        res[f"{tag}_int8_tops"] = round(fl * (s * (s + 1) // 2) / t / 1e9, 1)
+        res[f"{tag}_max_scaled_err_vs_native"] = rel
     nat.check(lib.mb_set_fp64_mode(ctx, 0, 7))
     out[str(n)] = res
     print(n, json.dumps(res), flush=True)

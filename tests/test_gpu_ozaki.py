@@ -23,7 +23,7 @@ def gpu():
     lib.mb_shutdown(ctx)
 
 
-def run(gpu, A, B, slices, C0=None):
+def run(gpu, A, B, slices, C0=None, mode=1):
     import torch
     lib, ctx = gpu
     m, k = A.shape
@@ -32,7 +32,7 @@ def run(gpu, A, B, slices, C0=None):
     dB = torch.from_numpy(np.ascontiguousarray(B.T)).cuda()
     dC = torch.from_numpy(np.ascontiguousarray(C0.T)).cuda() if C0 is not None else torch.full((n, m), float("nan"), dtype=torch.float64, device="cuda")
     torch.cuda.synchronize()
-    nat.check(lib.mb_set_fp64_mode(ctx, 1 if slices else 0, slices or 7))
+    nat.check(lib.mb_set_fp64_mode(ctx, mode if slices else 0, slices or 7))
     p = lambda t: C.c_void_p(t.data_ptr())
     nat.check(lib.mb_dgemm_device(ctx, b"N", b"N", m, n, k, 1.0, p(dA), m, p(dB), k, 1.0 if C0 is not None else 0.0, p(dC), m))
     nat.check(lib.mb_synchronize(ctx))
@@ -51,6 +51,24 @@ def test_int8_split_gemm_uniform_inputs(gpu, shape, slices):
     err = (np.abs(got - ref) / (np.abs(A) @ np.abs(B))).max()
     assert err <= {6: 2e-11, 7: 2e-13, 8: 5e-15}[slices], err
     assert np.linalg.norm(got - ref) / np.linalg.norm(ref) <= 1e-10
+
+
+@pytest.mark.parametrize("shape", [(256, 256, 256), (300, 520, 700), (1024, 768, 2048)])
+@pytest.mark.parametrize("slices", [5, 6])
+def test_int8_split_8bit_digits(gpu, shape, slices):
+    """8-bit digit planes (MB_FP64_INT8_SPLIT8): 5 planes = 38 fractional bits in 15 int8 GEMMs."""
+    m, n, k = shape
+    rng = np.random.default_rng(m * 3 + n + k)
+    A, B = rng.random((m, k)), rng.random((k, n))
+    ref = A @ B
+    got = run(gpu, A, B, slices, mode=2)
+    err = (np.abs(got - ref) / (np.abs(A) @ np.abs(B))).max()
+    assert err <= {5: 5e-11, 6: 5e-13}[slices], err
+    As = (rng.random((m, k)) - 0.5)
+    Bs = (rng.random((k, n)) - 0.5)
+    got = run(gpu, As, Bs, slices, mode=2)
+    scale = np.abs(As).max(axis=1)[:, None] * np.abs(Bs).max(axis=0)[None, :] * k
+    assert (np.abs(got - As @ Bs) / scale).max() <= {5: 1e-11, 6: 1e-13}[slices]
 
 
 def test_int8_split_signed_scaled_rows_and_accumulate(gpu):
