@@ -45,6 +45,12 @@ class Runtime:
         """Launch on torch's current stream so torch.distributed collectives and our kernels order correctly."""
         nat.check(self.lib.mb_set_stream(self.ctx, C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)))
 
+    def set_fp64_mode(self, mode: str = "native", slices: int = 6) -> None:
+        """'native' (DMMA, IEEE fp64 — default), 'int8x7' (int8 tensor cores, 7-bit digit planes) or 'int8x8'
+        (8-bit digit planes).  See include/marlin_b200.h: mb_set_fp64_mode."""
+        code = {"native": 0, "int8x7": 1, "int8x8": 2}[mode]
+        nat.check(self.lib.mb_set_fp64_mode(self.ctx, code, slices))
+
     def launch_count(self) -> int:
         return int(self.lib.mb_launch_count(self.ctx))
 
