@@ -39,6 +39,11 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--size", type=int, default=16384)
     ap.add_argument("--grid", type=int, default=2)
+    ap.add_argument("--dtype", default="f64", choices=["f64", "bf16"],
+                    help="tile element type: f64 (headline, configs[1..2]) or bf16 (configs[4]: --size 65536 --grid 4 --dtype bf16)")
+    ap.add_argument("--workload", default="blockmatrix", choices=["blockmatrix", "tallskinny"],
+                    help="blockmatrix: BlockMatrix x BlockMatrix (configs[1,2,4]); tallskinny: configs[3], DenseVecMatrix "
+                         "1048576x1024 row-sharded times a replicated 1024x1024 (DenseVecMatrix.multiply(B: BDM))")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -174,8 +179,23 @@ def run_ours(args):
     N, g = args.size, args.grid
     flops = 2.0 * N * N * N
 
-    A = mb.MTUtils.randomBlockMatrix(None, N, N, g, g, seed=42)
-    B = mb.MTUtils.randomBlockMatrix(None, N, N, g, g, seed=43)
+    bf16 = args.dtype == "bf16"
+    tall = args.workload == "tallskinny"
+    if tall:
+        rows_total, kdim = 1048576, 1024
+        A = mb.MTUtils.randomDenVecMatrix(None, rows_total, kdim, numPartitions=ws, seed=42)
+        Bsub = mb.MTUtils.randomBlockMatrix(None, kdim, kdim, 1, 1, seed=43)       # generated where block (0,0) lives ...
+        Bfull = Bsub.toBreeze()                                                   # ... and replicated (sc.broadcast)
+        B = mb.SubMatrix(Bfull)
+        flops = 2.0 * rows_total * kdim * kdim
+        args.no_e2e = True
+        args.no_int8_split = True
+    else:
+        A = mb.MTUtils.randomBlockMatrix(None, N, N, g, g, seed=42, dtype=nat.MB_BF16 if bf16 else nat.MB_F64)
+        B = mb.MTUtils.randomBlockMatrix(None, N, N, g, g, seed=43, dtype=nat.MB_BF16 if bf16 else nat.MB_F64)
+        if bf16:
+            args.no_e2e = True
+            args.no_int8_split = True
     torch.cuda.synchronize()
 
     def barrier():
@@ -184,7 +204,7 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     def step():
-        return A.multiply(B)                       # BlockMatrix.multiply(other: BlockMatrix)
+        return A.multiply(B)                       # BlockMatrix.multiply(other: BlockMatrix) / DenseVecMatrix.multiply(B: BDM)
 
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -218,12 +238,17 @@ def run_ours(args):
     # launching stream; algorithmic flops per launch = this rank's share of the 2*N^3 flops / its launches per step
     # (1 grouped launch when the rank holds whole kk-sums, else one launch per 8192^3 block product).
     bs = N // g
-    plan = comm.plan_multiply(g, g, g, ws, A.owner, B.owner)
-    local_products = len(plan.products.get(rank, []))
-    gemm_ms, gemm_n = phases.get("gemm", (0.0, 0))
+    if tall:
+        local_products, gemm_ms, gemm_n = 1, ms_total, args.steps          # one GEMM per row shard per step, nothing else
+        launches_per_step = 1
+        flops_per_launch = flops / ws
+    else:
+        plan = comm.plan_multiply(g, g, g, ws, A.owner, B.owner)
+        local_products = len(plan.products.get(rank, []))
+        gemm_ms, gemm_n = phases.get("gemm", (0.0, 0))
+        launches_per_step = max(1, gemm_n // max(1, args.steps))
+        flops_per_launch = local_products * 2.0 * bs ** 3 / launches_per_step
     gemm_avg_ms = gemm_ms / max(1, gemm_n)
-    launches_per_step = max(1, gemm_n // max(1, args.steps))
-    flops_per_launch = local_products * 2.0 * bs ** 3 / launches_per_step
     achieved = flops_per_launch / (gemm_avg_ms * 1e-3) / 1e12 if gemm_n else None
     traffic = None
     summary = ROOT / "profiles" / "ncu_summary.json"
@@ -232,11 +257,22 @@ def run_ours(args):
             traffic = json.loads(summary.read_text()).get("gemm_f64_dmma", {}).get("dram_bytes_per_launch")
         except Exception:
             traffic = None
-    roofline = {"bound": "tensor", "achieved": achieved, "peak": FP64_PEAK_TFLOPS_MEASURED, "unit": "TFLOP/s",
-                "frac": (achieved / FP64_PEAK_TFLOPS_MEASURED) if achieved else None, "traffic": traffic,
-                "kernel": ("gemm_f64_dmma_grouped_kernel" if launches_per_step < local_products else "gemm_f64_dmma_kernel<N,N>") + " (DMMA.8x8x4 + TMA)", "launch_ms_avg": gemm_avg_ms,
+    peak, peak_src = FP64_PEAK_TFLOPS_MEASURED, None
+    if bf16:
+        try:
+            peak = float(json.loads((ROOT / "MEASURED_PEAKS.json").read_text())["bf16_tflops_sustained"])
+            peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (cuBLAS bf16, seconds-long loop)"
+        except Exception:
+            peak, peak_src = 1400.0, "fallback sustained bf16 figure of B200_PROFILING.md"
+        traffic = None
+    roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                "frac": (achieved / peak) if achieved else None, "traffic": traffic,
+                "kernel": ("gemm_bf16_tcgen05_kernel<N,N> (tcgen05.mma kind::f16 + TMEM + TMA)" if bf16 else
+                           ("gemm_f64_dmma_kernel<T,N> (row-major C = A*B as C^T = B^T*A^T)" if tall else
+                            ("gemm_f64_dmma_grouped_kernel" if launches_per_step < local_products else "gemm_f64_dmma_kernel<N,N>")
+                            + " (DMMA.8x8x4 + TMA)")), "launch_ms_avg": gemm_avg_ms,
                 "flops_per_launch": flops_per_launch, "launches_per_step": launches_per_step,
-                "peak_source": "measured fp64 DMMA issue peak on this pool's B200 (scripts/dmma_bench.cu, "
+                "peak_source": peak_src or "measured fp64 DMMA issue peak on this pool's B200 (scripts/dmma_bench.cu, "
                                "profiles/r01_probe_dmma_peak_and_gemm_v1.log); MEASURED_PEAKS.json carries no fp64 entry; "
                                "cuBLAS dgemm on the same GPU measured 36.2 TFLOP/s"}
 
@@ -312,9 +348,9 @@ def run_ours(args):
     int8_split = None
     if ws == 1 and not args.no_int8_split:
         try:
-            slices = 6
+            slices = 5                                          # 8-bit digits x 5 planes = 38 bits, 15 int8 GEMMs
             Cn = A.multiply(B)                                  # native result, kept for the error check
-            rt.set_fp64_mode("int8x7", slices)
+            rt.set_fp64_mode("int8x8", slices)
             for _ in range(2):
                 Cs = A.multiply(B)
             torch.cuda.synchronize()
@@ -330,7 +366,7 @@ def run_ours(args):
                 a_, b_ = sn.buf[: sn.rows * sn.cols], ss.buf[: ss.rows * ss.cols]
                 errs.append(((a_ - b_).abs() / a_.abs()).max().item())     # U[0,1) inputs: C_ij = (|A||B|)_ij
             int8_split = {"value": flops / (ms * 1e-3) / 1e12, "unit": "TFLOP/s (fp64-equivalent)", "ms_per_step": ms,
-                          "digit_planes": slices, "int8_gemms_per_product": slices * (slices + 1) // 2,
+                          "digit_bits": 8, "digit_planes": slices, "int8_gemms_per_product": slices * (slices + 1) // 2,
                           "int8_tops": flops * (slices * (slices + 1) // 2) / (ms * 1e-3) / 1e12,
                           "max_err_vs_native_scaled_by_absA_absB": max(errs), "tolerance": 1e-10,
                           "kernel": "gemm_ozaki_i8_kernel (tcgen05.mma.kind::i8, TMEM int32 accumulators) + split kernels",
@@ -349,20 +385,32 @@ def run_ours(args):
         par = {1: "1 GPU: all 8 block products local, k-sum accumulated in the GEMM epilogue",
                2: "2 GPUs: 4 products each, k-sum local", 4: "4 GPUs: 2 products each (same C tile), k-sum local",
                8: "8 GPUs: 1 product each (RDD partition == GPU), A/B tiles via grouped NCCL send/recv, pairwise reduce of partials"}
+        metric = METRIC
+        workload = (f"{N}x{N} fp64 BlockMatrix multiply, {g}x{g} block grid, (m,k,n)=({g},{g},{g}) "
+                    f"[BASELINE.json configs[2]; also the 1-GPU target size]")
+        if tall:
+            metric = "fp64 tall-skinny multiply throughput (2*M*K*N flop), DenseVecMatrix 1048576x1024 x 1024x1024"
+            workload = "DenseVecMatrix 1048576x1024 (row-sharded) x replicated 1024x1024, fp64 [BASELINE.json configs[3]]"
+        elif bf16:
+            metric = f"bf16 dense multiply throughput (2*N^3 flop), {N}x{N} BlockMatrix {g}x{g} grid"
+            workload = f"{N}x{N} bf16 BlockMatrix multiply, {g}x{g} block grid, fp32 accumulate / fp32 C tiles [BASELINE.json configs[4]]"
+        elif (N, g) != (16384, 2):
+            metric = f"fp64 dense multiply throughput (2*N^3 flop), {N}x{N} BlockMatrix {g}x{g} grid"
+            workload = f"{N}x{N} fp64 BlockMatrix multiply, {g}x{g} block grid"
         line = {
-            "metric": METRIC, "value": value, "unit": "TFLOP/s", "n_gpus": ws, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "metric": metric, "value": value, "unit": "TFLOP/s", "n_gpus": ws, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "bf16" if bf16 else "f64",
             "data": "synthetic",
-            "config": {"workload": f"{N}x{N} fp64 BlockMatrix multiply, {g}x{g} block grid, (m,k,n)=({g},{g},{g}) "
-                                   f"[BASELINE.json configs[2]; also the 1-GPU target size]",
-                       "parallelism": par.get(ws, f"{ws} GPUs"),
+            "config": {"workload": workload,
+                       "parallelism": par.get(ws, f"{ws} GPUs") if not (tall or bf16 or (N, g) != (16384, 2)) else f"{ws} GPU(s), one process each",
                        "l2": "inputs (2 GiB per operand) are far larger than the 126 MB L2; no explicit flush",
                        "inputs": "U[0,1) fp64 from the on-device XORShift generator (MTUtils.randomBlockMatrix, seeds 42/43)"},
             "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu_baseline, "gpu_launches": int(launches),
             "fp64_on_int8_tensor_cores": int8_split,
             "clocks": clocks,
             "phases_ms_per_step": {k: v[0] / args.steps for k, v in phases.items()},
-            "pct_of_fp64_peak": 100.0 * value / (FP64_PEAK_TFLOPS_MEASURED * ws),
+            "pct_of_tensor_peak": 100.0 * value / (peak * ws),
         }
         print(json.dumps(line), flush=True)
     if ws > 1:
