@@ -310,26 +310,46 @@ __device__ unsigned long long xs_jump(unsigned long long s, unsigned long long s
 // block writes its 8192 values with coalesced stores.  The jump is hierarchical: every thread applies the block's
 // base offset (shared bits of the step count) plus its own t*2*FILL_CHUNK steps.
 constexpr int FILL_CHUNK = 16;   // values per thread (256 x 17 x 8 B = 34 KiB of static smem)
-constexpr int FILL_LO = 5, FILL_LEVELS = 8;   // thread offset = tid * 2 * FILL_CHUNK steps = tid << 5: bits 5..12
+__device__ unsigned long long g_jump[40][64];      // same tables in global memory: lane-parallel (coalesced) access
+
+// T^steps * s computed by a whole warp: lane l owns columns l and l+32 of each power-of-two matrix, the partial XORs
+// are combined with shuffles.  ~25 instructions per set bit of `steps` instead of a 64-iteration serial loop.
+__device__ __forceinline__ unsigned long long xs_jump_warp(unsigned long long s, unsigned long long steps, int lane) {
+    for (int j = 0; j < 40 && steps; ++j, steps >>= 1) {
+        if (steps & 1ull) {
+            unsigned long long v = ((s >> lane) & 1ull) ? g_jump[j][lane] : 0ull;
+            v ^= ((s >> (lane + 32)) & 1ull) ? g_jump[j][lane + 32] : 0ull;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v ^= __shfl_xor_sync(0xffffffffu, v, o);
+            s = v;
+        }
+    }
+    return s;
+}
+
+// Block = 256 threads; thread (warp w, lane l) generates FILL_CHUNK consecutive values starting at value
+// block_first + (32 w + l) * FILL_CHUNK.  Jump = block base (warp-parallel) + warp part (warp-parallel)
+// + lane part (<= 5 serial levels from shared-memory tables), then coalesced write-out through shared memory.
+constexpr int FILL_LANE_LO = 5;     // lane offset = l * 2 * FILL_CHUNK steps = l << 5 : table levels 5..9
 __global__ void __launch_bounds__(256) fill_uniform_kernel(double* out, long long rs, long long cs, int rows, int cols,
                                                           int row_major, unsigned long long state0, long long first,
                                                           double lo, double hi) {
     __shared__ double stage[256][FILL_CHUNK + 1];
-    __shared__ unsigned long long jump_s[FILL_LEVELS][64];   // lane-divergent lookups: shared memory, not __constant__
-    __shared__ unsigned long long base_state;
+    __shared__ unsigned long long jump_s[5][64];
     const long long total = (long long)rows * cols;
     const long long block_first = (long long)blockIdx.x * 256 * FILL_CHUNK;
     if (block_first >= total) return;
-    for (int e = threadIdx.x; e < FILL_LEVELS * 64; e += 256) jump_s[e >> 6][e & 63] = c_jump[FILL_LO + (e >> 6)][e & 63];
-    if (threadIdx.x == 0) base_state = xs_jump(state0, 2ull * (unsigned long long)(first + block_first));
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int e = threadIdx.x; e < 5 * 64; e += 256) jump_s[e >> 6][e & 63] = g_jump[FILL_LANE_LO + (e >> 6)][e & 63];
+    // every warp: base jump to its own first value (block base + 32 * warp chunks), cooperatively
+    unsigned long long s = xs_jump_warp(state0, 2ull * (unsigned long long)(first + block_first + (long long)warp * 32 * FILL_CHUNK), lane);
     __syncthreads();
     const long long i0 = block_first + (long long)threadIdx.x * FILL_CHUNK;
     const double span = __dsub_rn(hi, lo);
     if (i0 < total) {
-        unsigned long long s = base_state;
-        unsigned steps = threadIdx.x;             // in units of 2^FILL_LO xorshift steps
+        unsigned steps = lane;                     // in units of 2^FILL_LANE_LO xorshift steps
 #pragma unroll 1
-        for (int j = 0; j < FILL_LEVELS && steps; ++j, steps >>= 1) {
+        for (int j = 0; j < 5 && steps; ++j, steps >>= 1) {
             if (steps & 1u) {
                 unsigned long long t = 0, x = s;
                 while (x) {
@@ -515,6 +535,7 @@ cudaError_t fill_uniform_init_tables() {
         built = true;
     }
     cudaError_t e = cudaMemcpyToSymbol(c_jump, tab, sizeof(tab));
+    if (e == cudaSuccess) e = cudaMemcpyToSymbol(g_jump, tab, sizeof(tab));
     if (e == cudaSuccess && dev >= 0 && dev < 64) done[dev] = true;
     return e;
 }
