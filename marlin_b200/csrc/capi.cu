@@ -595,6 +595,23 @@ int32_t mb_matmul_blocked_subset(mb_ctx* ctx, mb_block* const* A_tiles, mb_block
     //      (reduceByKey at :177) accumulated in place, kk ascending ----
     for (int c = 0; c < num_c; ++c) {
         const int id = c_ids[c], i = id / n, j = id % n;
+        mb_block* cb = C_tiles[id];
+        // bf16 tiles: fold the kk-sum into ONE tcgen05 launch per C block (K segments; accumulator stays in TMEM)
+        bool seg_ok = k <= 8 && !cb->is_transpose && (cb->dtype == MB_F32 || cb->dtype == MB_BF16);
+        const void* Ap[8]; const void* Bp[8]; long long la[8], lb[8]; int Ks[8];
+        for (int kk = 0; kk < k && seg_ok; ++kk) {
+            const mb_block *a = A_tiles[i * k + kk], *b = B_tiles[kk * n + j];
+            seg_ok = a->dtype == MB_BF16 && b->dtype == MB_BF16 && !a->is_transpose && !b->is_transpose && a->cols > 0;
+            Ap[kk] = elem_ptr(a); Bp[kk] = elem_ptr(b); la[kk] = a->ld; lb[kk] = b->ld; Ks[kk] = a->cols;
+        }
+        if (seg_ok) {
+            int launches = 0;
+            cudaError_t e = mb::gemm_bf16_segments(false, false, cb->rows, cb->cols, k, Ks, Ap, la, Bp, lb, elem_ptr(cb), cb->ld,
+                                                   cb->dtype == MB_F32, false, ctx->num_sms, ctx->stream, &launches);
+            if (e == cudaSuccess) { ctx->launches += launches; continue; }
+            if (e != cudaErrorNotSupported) return cuda_fail(e, "gemm_bf16_segments");
+            cudaGetLastError();
+        }
         for (int kk = 0; kk < k; ++kk) {
             int32_t r = mb_block_gemm(ctx, A_tiles[i * k + kk], B_tiles[kk * n + j], C_tiles[id], kk > 0);
             if (r) return r;

@@ -34,6 +34,16 @@ constexpr int NUM_THREADS = 192;
 constexpr int SMEM_BYTES = NUM_STAGES * STAGE_BYTES + 1024 + 256;
 constexpr int BAND = 16;
 
+constexpr int MAX_SEG = 8;
+// K segments: C = sum over seg of op(A_seg) * op(B_seg).  One segment for a plain GEMM; k of them when the kk-sum of a
+// blocked multiply (matrix/BlockMatrix.scala:177) is folded into ONE launch, so the fp32 accumulator never leaves TMEM.
+struct SegMaps {
+    CUtensorMap a[MAX_SEG];
+    CUtensorMap b[MAX_SEG];
+    int num_kb[MAX_SEG];
+    int nseg;
+};
+
 struct Params {
     int M, N, K;
     void* C;
@@ -113,8 +123,7 @@ __host__ __device__ constexpr uint32_t instr_desc(bool a_mn_major, bool b_mn_maj
 
 template <bool TA, bool TB>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
-                         const Params p) {
+gemm_bf16_tcgen05_kernel(const __grid_constant__ SegMaps maps, const Params p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t bar_base = smem_base + NUM_STAGES * STAGE_BYTES;
@@ -128,14 +137,15 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int num_tiles = p.tiles_m * p.tiles_n;
-    const int num_kb = (p.K + BK - 1) / BK;
+    int num_kb = 0;                     // k-slabs of all segments
+    for (int sg = 0; sg < maps.nseg; ++sg) num_kb += maps.num_kb[sg];
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < NUM_STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
         for (int a = 0; a < NUM_ACC; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, 4); }
         fence_barrier_init();
-        tma_prefetch_desc(&mapA);
-        tma_prefetch_desc(&mapB);
+        tma_prefetch_desc(&maps.a[0]);
+        tma_prefetch_desc(&maps.b[0]);
     }
     if (warp == 1) {
         tmem_alloc(tmem_slot, NUM_ACC * BN);
@@ -155,26 +165,31 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_
                 int tm, tn;
                 tile_coords(t, p.tiles_m, p.tiles_n, tm, tn);
                 const int m0 = tm * BM, n0 = tn * BN;
-                for (int kb = 0; kb < num_kb; ++kb) {
-                    mbar_wait(bar_empty + 8 * stage, phase ^ 1);
-                    const uint32_t full = bar_full + 8 * stage;
-                    const uint32_t sA = smem_base + stage * STAGE_BYTES;
-                    const uint32_t sB = sA + A_BYTES;
-                    mbar_arrive_expect_tx(full, STAGE_BYTES);
-                    const int k0 = kb * BK;
-                    if (!TA) {
-                        tma_load_2d(sA, &mapA, full, m0, k0);
-                        tma_load_2d(sA + 8192, &mapA, full, m0 + 64, k0);
-                    } else {
-                        tma_load_2d(sA, &mapA, full, k0, m0);
-                    }
-                    if (!TB) {
-                        tma_load_2d(sB, &mapB, full, k0, n0);
-                    } else {
+                for (int sg = 0; sg < maps.nseg; ++sg) {
+                    const CUtensorMap* mapA = &maps.a[sg];
+                    const CUtensorMap* mapB = &maps.b[sg];
+                    const int nkb = maps.num_kb[sg];
+                    for (int kb = 0; kb < nkb; ++kb) {
+                        mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+                        const uint32_t full = bar_full + 8 * stage;
+                        const uint32_t sA = smem_base + stage * STAGE_BYTES;
+                        const uint32_t sB = sA + A_BYTES;
+                        mbar_arrive_expect_tx(full, STAGE_BYTES);
+                        const int k0 = kb * BK;
+                        if (!TA) {
+                            tma_load_2d(sA, mapA, full, m0, k0);
+                            tma_load_2d(sA + 8192, mapA, full, m0 + 64, k0);
+                        } else {
+                            tma_load_2d(sA, mapA, full, k0, m0);
+                        }
+                        if (!TB) {
+                            tma_load_2d(sB, mapB, full, k0, n0);
+                        } else {
 #pragma unroll
-                        for (int b = 0; b < 4; ++b) tma_load_2d(sB + b * 8192, &mapB, full, n0 + 64 * b, k0);
+                            for (int b = 0; b < 4; ++b) tma_load_2d(sB + b * 8192, mapB, full, n0 + 64 * b, k0);
+                        }
+                        if (++stage == NUM_STAGES) { stage = 0; phase ^= 1; }
                     }
-                    if (++stage == NUM_STAGES) { stage = 0; phase ^= 1; }
                 }
             }
         }
@@ -237,14 +252,21 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_
                 if (m_ok) {
                     if (p.c_is_f32) {
                         float* crow = static_cast<float*>(p.C) + m;
+                        float old[32];
+                        if (p.accumulate) {      // all 32 loads first: one memory latency per chunk, not 32 dependent ones
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) {
+                                const int n = n0 + c * 32 + j;
+                                old[j] = (n < p.N) ? __ldcg(crow + (long long)n * p.ldc) : 0.f;
+                            }
+                        }
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
                             const int n = n0 + c * 32 + j;
                             if (n < p.N) {
                                 float x = __uint_as_float(v[j]);
-                                float* dst = crow + (long long)n * p.ldc;
-                                if (p.accumulate) x += *dst;
-                                *dst = x;
+                                if (p.accumulate) x += old[j];
+                                crow[(long long)n * p.ldc] = x;
                             }
                         }
                     } else {
@@ -305,7 +327,7 @@ bool make_map_bf16(CUtensorMap* map, const void* base, uint64_t dim0, uint64_t d
 }
 
 template <bool TA, bool TB>
-cudaError_t launch(const CUtensorMap& mA, const CUtensorMap& mB, const Params& p, int num_sms, cudaStream_t stream) {
+cudaError_t launch(const SegMaps& maps, const Params& p, int num_sms, cudaStream_t stream) {
     auto kern = gemm_bf16_tcgen05_kernel<TA, TB>;
     static bool attr_done = false;
     if (!attr_done) {
@@ -314,36 +336,53 @@ cudaError_t launch(const CUtensorMap& mA, const CUtensorMap& mB, const Params& p
         attr_done = true;
     }
     const int grid = min(p.tiles_m * p.tiles_n, num_sms);
-    kern<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(mA, mB, p);
+    kern<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(maps, p);
     return cudaGetLastError();
 }
 
 }  // namespace
+
+cudaError_t gemm_bf16_segments(bool transA, bool transB, int M, int N, int nseg, const int* Kseg, const void* const* A,
+                               const long long* lda, const void* const* B, const long long* ldb, void* C, long long ldc,
+                               bool c_is_f32, bool accumulate, int num_sms, cudaStream_t stream, int* launches) {
+    if (M <= 0 || N <= 0) return cudaSuccess;
+    if (nseg <= 0 || nseg > MAX_SEG || !get_encode_fn()) return cudaErrorNotSupported;
+    static thread_local SegMaps maps;
+    maps.nseg = nseg;
+    int Ktot = 0;
+    for (int sg = 0; sg < nseg; ++sg) {
+        const int K = Kseg[sg];
+        if (K <= 0) return cudaErrorNotSupported;
+        const bool aligned = ((reinterpret_cast<uintptr_t>(A[sg]) | reinterpret_cast<uintptr_t>(B[sg])) & 15) == 0 &&
+                             (lda[sg] % 8 == 0) && (ldb[sg] % 8 == 0);
+        if (!aligned) return cudaErrorNotSupported;
+        bool ok = true;
+        ok = ok && (!transA ? make_map_bf16(&maps.a[sg], A[sg], M, K, lda[sg], 64, 64) : make_map_bf16(&maps.a[sg], A[sg], K, M, lda[sg], 64, 128));
+        ok = ok && (!transB ? make_map_bf16(&maps.b[sg], B[sg], K, N, ldb[sg], 64, 256) : make_map_bf16(&maps.b[sg], B[sg], N, K, ldb[sg], 64, 64));
+        if (!ok) return cudaErrorNotSupported;
+        maps.num_kb[sg] = (K + BK - 1) / BK;
+        Ktot += K;
+    }
+    Params p;
+    p.M = M; p.N = N; p.K = Ktot; p.C = C; p.ldc = ldc;
+    p.tiles_m = (M + BM - 1) / BM;
+    p.tiles_n = (N + BN - 1) / BN;
+    p.c_is_f32 = c_is_f32 ? 1 : 0;
+    p.accumulate = accumulate ? 1 : 0;
+    if (launches) ++*launches;
+    if (!transA && !transB) return launch<false, false>(maps, p, num_sms, stream);
+    if (transA && !transB) return launch<true, false>(maps, p, num_sms, stream);
+    if (!transA && transB) return launch<false, true>(maps, p, num_sms, stream);
+    return launch<true, true>(maps, p, num_sms, stream);
+}
 
 cudaError_t gemm_bf16(bool transA, bool transB, int M, int N, int K, const void* A, long long lda, const void* B,
                       long long ldb, void* C, long long ldc, bool c_is_f32, bool accumulate, int num_sms,
                       cudaStream_t stream, int* launches) {
     if (M <= 0 || N <= 0) return cudaSuccess;
     if (K <= 0) return accumulate ? cudaSuccess : cudaErrorNotSupported;
-    const bool aligned = ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B)) & 15) == 0 && (lda % 8 == 0) &&
-                         (ldb % 8 == 0);
-    if (!aligned || !get_encode_fn()) return cudaErrorNotSupported;
-    CUtensorMap mA, mB;
-    bool ok = true;
-    ok = ok && (!transA ? make_map_bf16(&mA, A, M, K, lda, 64, 64) : make_map_bf16(&mA, A, K, M, lda, 64, 128));
-    ok = ok && (!transB ? make_map_bf16(&mB, B, K, N, ldb, 64, 256) : make_map_bf16(&mB, B, N, K, ldb, 64, 64));
-    if (!ok) return cudaErrorNotSupported;
-    Params p;
-    p.M = M; p.N = N; p.K = K; p.C = C; p.ldc = ldc;
-    p.tiles_m = (M + BM - 1) / BM;
-    p.tiles_n = (N + BN - 1) / BN;
-    p.c_is_f32 = c_is_f32 ? 1 : 0;
-    p.accumulate = accumulate ? 1 : 0;
-    if (launches) ++*launches;
-    if (!transA && !transB) return launch<false, false>(mA, mB, p, num_sms, stream);
-    if (transA && !transB) return launch<true, false>(mA, mB, p, num_sms, stream);
-    if (!transA && transB) return launch<false, true>(mA, mB, p, num_sms, stream);
-    return launch<true, true>(mA, mB, p, num_sms, stream);
+    return gemm_bf16_segments(transA, transB, M, N, 1, &K, &A, &lda, &B, &ldb, C, ldc, c_is_f32, accumulate, num_sms, stream,
+                              launches);
 }
 
 }  // namespace mb

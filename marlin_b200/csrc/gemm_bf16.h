@@ -10,4 +10,10 @@ cudaError_t gemm_bf16(bool transA, bool transB, int M, int N, int K, const void*
                       long long ldb, void* C, long long ldc, bool c_is_f32, bool accumulate, int num_sms,
                       cudaStream_t stream, int* launches);
 
+// The same with the contraction split into `nseg` (<= 8) segments: C = sum_s op(A_s) * op(B_s).  Used to fold the kk-sum
+// of a blocked multiply into one launch per C block (the accumulator stays in TMEM; no read-modify-write of C).
+cudaError_t gemm_bf16_segments(bool transA, bool transB, int M, int N, int nseg, const int* Kseg, const void* const* A,
+                               const long long* lda, const void* const* B, const long long* ldb, void* C, long long ldc,
+                               bool c_is_f32, bool accumulate, int num_sms, cudaStream_t stream, int* launches);
+
 }  // namespace mb
