@@ -145,8 +145,7 @@ class BlockMatrix(DistributedMatrix):
             if isinstance(other, DenseVecMatrix):
                 # reference quirk (:97-98): evaluates that.multiply(this.toBreeze()), i.e. B * A_local
                 return other.multiply(self.toBreeze())
-            raise nat.MarlinArgumentError(nat.MB_ERR_UNSUPPORTED, "multiplyBy (BlockMatrix.scala:309-335) is outside the "
-                                          "hot-path scope of this engine")
+            return other.multiplyBy(self.toBreeze())                             # :114-115
         return self._multiply_split(other, (mkn[0], mkn[1], mkn[2]))
 
     def _multiply_split(self, other, splitMode: Tuple[int, int, int]) -> "BlockMatrix":
@@ -512,6 +511,28 @@ class BlockMatrix(DistributedMatrix):
         # the reference reports numBlksByCol() although every key has column 0 (:301); kept
         return BlockMatrix(res, self.numRows(), b_cols, self.numBlksByRow(), self.numBlksByCol(),
                            placement=(lambda r, c, s=self: s.owner(r, 0)) if ws > 1 else None)
+
+    def multiplyBy(self, B) -> "BlockMatrix":
+        """multiplyBy(B: BDM[Double]) :309-335 — a small local matrix times this block matrix (B replicated on every
+        rank).  One block row: B * blk per block.  Several block rows: B(::, cols of block-row r) * blk, summed over r
+        (reduceByKey on the unchanged BlockID, i.e. onto the block of row 0 ... as written, the keys keep their row, so
+        only blocks with equal ids are summed — with distinct ids nothing is summed; reproduced as is)."""
+        Bd = B if isinstance(B, SubMatrix) else SubMatrix(B)
+        if Bd.cols != self.numRows():
+            raise nat.MarlinArgumentError(nat.MB_ERR_DIM_MISMATCH, "Dimension mismatch during matrix-matrix multiplication: "
+                                          f"{Bd.cols} vs {self.numRows()}")
+        if self.numBlksByRow() == 1:
+            res = [(b, Bd.multiply(blk)) for b, blk in self.blocks]                       # :315-319
+            # the reference labels the result numRows() x B.cols (:319); the data is B.rows x numCols()
+            return BlockMatrix(res, Bd.rows, self.numCols(), self.numBlksByRow(), self.numBlksByCol(), self._placement)
+        row_blk = _ceil_len(self.numRows(), self.numBlksByRow())
+        res = []
+        for b, blk in self.blocks:
+            start = b.row * row_blk
+            end = self.numCols() if (b.row + 1) * row_blk > self.numCols() else (b.row + 1) * row_blk      # :324 bounds by numCols()
+            end = min(end, Bd.cols)
+            res.append((b, Bd.slice(0, Bd.rows, start, end).multiply(blk)))                               # :330-331
+        return BlockMatrix(res, Bd.rows, self.numCols(), self.numBlksByRow(), self.numBlksByCol(), self._placement)
 
     def _reduce_row_partials(self, acc: Dict[int, SubMatrix]) -> Dict[int, SubMatrix]:
         """reduceByKey over column blocks held by different ranks (:300): partials go to owner(row, 0)."""

@@ -138,8 +138,7 @@ class DenseVecMatrix(DistributedMatrix):
             if isinstance(other, DenseVecMatrix):
                 # reference quirk (:206-207): that.multiply(this.toBreeze()) evaluates B * A_local
                 return other._multiply_local(self.toBreeze())
-            raise nat.MarlinArgumentError(nat.MB_ERR_UNSUPPORTED, "multiplyBy (BlockMatrix.scala:309-335) is outside the "
-                                          "hot-path scope of this engine")
+            return other.multiplyBy(self.toBreeze())                             # :223-224
         return self._multiply_split(other, (mkn[0], mkn[1], mkn[2]))
 
     def _multiply_split(self, other, splitMode: Tuple[int, int, int]):

@@ -233,3 +233,21 @@ def test_save_and_load_block_format(M, tmp_path):
     assert np.array_equal(again.toBreeze(), mc.EXPECTED_DENSE)
     dvm(M).saveToFileSystem(str(tmp_path / "rows"))
     assert np.array_equal(M.MTUtils.loadMatrixFile(None, str(tmp_path / "rows")).toBreeze(), mc.EXPECTED_DENSE)
+
+
+def test_multiply_by_local_matrix(M):
+    """BlockMatrix.multiplyBy(B: BDM) (BlockMatrix.scala:309-319), the small-A arm of the chooser (:114-115,
+    DenseVecMatrix.scala:223-224): one block row, B * blk per block."""
+    rng = np.random.default_rng(31)
+    Bl = rng.integers(-3, 4, size=(5, 6)).astype(float)
+    X = rng.integers(-3, 4, size=(6, 8)).astype(float)
+    bm = M.DenseVecMatrix(list(enumerate(X))).toBlockMatrix(1, 2)
+    got = bm.multiplyBy(Bl)
+    assert np.array_equal(got.toBreeze(), Bl @ X)
+    # chooser: this (small DenseVecMatrix, 5x6) times a BlockMatrix too big to broadcast -> that.multiplyBy(this.toBreeze())
+    Xw = rng.integers(-3, 4, size=(6, 30000)).astype(float)         # 180000 elements > 1 MB / 8 = 131072
+    wide = M.DenseVecMatrix(list(enumerate(Xw))).toBlockMatrix(1, 2)
+    small = M.DenseVecMatrix(list(enumerate(Bl)))
+    res = small.multiply(wide, 2, 1)                   # broadcastThreshold = 1 MB: B too big to broadcast, A small
+    assert isinstance(res, M.BlockMatrix)
+    assert np.array_equal(res.toBreeze(), Bl @ Xw)
