@@ -370,13 +370,19 @@ __global__ void __launch_bounds__(256) fill_uniform_kernel(double* out, long lon
         }
     }
     __syncthreads();
-    const long long block_cnt = min((long long)256 * FILL_CHUNK, total - block_first);
-    for (long long e = threadIdx.x; e < block_cnt; e += 256) {
-        const long long i = block_first + e;
-        const double v = stage[e / FILL_CHUNK][e % FILL_CHUNK];
-        long long r, c;
-        if (row_major) { r = i / cols; c = i - r * cols; } else { c = i / rows; r = i - c * rows; }
-        out[r * rs + c * cs] = v;
+    const int block_cnt = (int)min((long long)256 * FILL_CHUNK, total - block_first);
+    // storage contiguous in fill order (a row-major shard filled row-major, or a packed column-major block filled
+    // column-major): linear index == storage index, no 64-bit divisions on the store path
+    const bool linear = row_major ? (cs == 1 && rs == cols) : (rs == 1 && cs == rows);
+    if (linear) {
+        for (int e = threadIdx.x; e < block_cnt; e += 256) out[block_first + e] = stage[e / FILL_CHUNK][e % FILL_CHUNK];
+    } else {
+        for (int e = threadIdx.x; e < block_cnt; e += 256) {
+            const long long i = block_first + e;
+            long long r, c;
+            if (row_major) { r = i / cols; c = i - r * cols; } else { c = i / rows; r = i - c * rows; }
+            out[r * rs + c * cs] = stage[e / FILL_CHUNK][e % FILL_CHUNK];
+        }
     }
 }
 
