@@ -673,23 +673,76 @@ int32_t mb_matmul_blocked_host(mb_ctx* ctx, const double* const* A_host, const d
     e = cudaEventCreateWithFlags(&ev_start, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventRecord(ev_start, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->h2d_stream, ev_start, 0);
+    // one block product restricted to columns [c0, c1) of B(kk,j) / C(i,j)
+    auto gemm_cols = [&](int i, int j, int kk, int c0, int c1) {
+        const int lda8 = even(row_len[i]) > 0 ? even(row_len[i]) : 1, ldb8 = even(k_len[kk]) > 0 ? even(k_len[kk]) : 1;
+        rc = dgemm_device_impl(ctx, 'N', 'N', row_len[i], c1 - c0, k_len[kk], 1.0, reinterpret_cast<double*>(base + offA[i * k + kk]), lda8,
+                               reinterpret_cast<double*>(base + offB[kk * n + j]) + (size_t)c0 * ldb8, ldb8, kk > 0 ? 1.0 : 0.0,
+                               reinterpret_cast<double*>(base + offC[i * n + j]) + (size_t)c0 * lda8, lda8, false);
+    };
+    std::vector<cudaEvent_t> chunk_events;
     for (int i = 0; i < m && e == cudaSuccess && rc == MB_OK; ++i)
         for (int j = 0; j < n && e == cudaSuccess && rc == MB_OK; ++j) {
             for (int kk = 0; kk < k && e == cudaSuccess && rc == MB_OK; ++kk) {
+                const bool first_product = (i == 0 && j == 0 && kk == 0);
+                const bool last_product = (i == m - 1 && j == n - 1 && kk == k - 1);
+                const int nch = ((first_product || last_product) && col_len[j] >= 1024) ? 4 : 1;
                 // uploads in first-use order (seq = i*n*k + j*k + kk)
                 upload(true, i * k + kk, row_len[i], k_len[kk], A_host[i * k + kk], offA[i * k + kk], evA[i * k + kk]);
-                upload(false, kk * n + j, k_len[kk], col_len[j], B_host[kk * n + j], offB[kk * n + j], evB[kk * n + j]);
                 if (e != cudaSuccess) break;
                 e = cudaStreamWaitEvent(ctx->stream, evA[i * k + kk], 0);
-                if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->stream, evB[kk * n + j], 0);
                 if (e != cudaSuccess) break;
-                rc = dgemm_device_impl(ctx, 'N', 'N', row_len[i], col_len[j], k_len[kk], 1.0,
-                                       reinterpret_cast<double*>(base + offA[i * k + kk]), even(row_len[i]) > 0 ? even(row_len[i]) : 1,
-                                       reinterpret_cast<double*>(base + offB[kk * n + j]), even(k_len[kk]) > 0 ? even(k_len[kk]) : 1,
-                                       kk > 0 ? 1.0 : 0.0, reinterpret_cast<double*>(base + offC[i * n + j]),
-                                       even(row_len[i]) > 0 ? even(row_len[i]) : 1, false);
+                if (nch == 1) {
+                    upload(false, kk * n + j, k_len[kk], col_len[j], B_host[kk * n + j], offB[kk * n + j], evB[kk * n + j]);
+                    if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->stream, evB[kk * n + j], 0);
+                    if (e != cudaSuccess) break;
+                    gemm_cols(i, j, kk, 0, col_len[j]);
+                    continue;
+                }
+                // The first product starts after A + a quarter of B has landed (B uploaded and multiplied in column
+                // chunks); the last product hands each finished column chunk of C to the D2H stream at once.
+                const bool b_pending = (evB[kk * n + j] == nullptr);
+                const int ldb8 = even(k_len[kk]), ldc8 = even(row_len[i]);
+                for (int q = 0; q < nch && e == cudaSuccess && rc == MB_OK; ++q) {
+                    const int c0 = (int)((long long)col_len[j] * q / nch), c1 = (int)((long long)col_len[j] * (q + 1) / nch);
+                    if (b_pending) {
+                        cudaEvent_t ev = nullptr;
+                        e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+                        if (e != cudaSuccess) break;
+                        chunk_events.push_back(ev);
+                        e = cudaMemcpy2DAsync(base + offB[kk * n + j] + (size_t)c0 * ldb8 * 8, (size_t)ldb8 * 8,
+                                              B_host[kk * n + j] + (size_t)c0 * k_len[kk], (size_t)k_len[kk] * 8, (size_t)k_len[kk] * 8,
+                                              c1 - c0, cudaMemcpyHostToDevice, ctx->h2d_stream);
+                        if (e == cudaSuccess) e = cudaEventRecord(ev, ctx->h2d_stream);
+                        if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->stream, ev, 0);
+                        if (e != cudaSuccess) break;
+                        if (q == nch - 1) {          // later users of this B tile wait for the whole of it
+                            e = cudaEventCreateWithFlags(&evB[kk * n + j], cudaEventDisableTiming);
+                            if (e == cudaSuccess) e = cudaEventRecord(evB[kk * n + j], ctx->h2d_stream);
+                        }
+                    } else if (q == 0) {
+                        e = cudaStreamWaitEvent(ctx->stream, evB[kk * n + j], 0);
+                    }
+                    if (e != cudaSuccess) break;
+                    gemm_cols(i, j, kk, c0, c1);
+                    if (rc != MB_OK) break;
+                    if (last_product) {
+                        cudaEvent_t ev = nullptr;
+                        e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+                        if (e != cudaSuccess) break;
+                        chunk_events.push_back(ev);
+                        e = cudaEventRecord(ev, ctx->stream);
+                        if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->d2h_stream, ev, 0);
+                        if (e == cudaSuccess && row_len[i] > 0 && c1 > c0)
+                            e = cudaMemcpy2DAsync(C_host[i * n + j] + (size_t)c0 * row_len[i], (size_t)row_len[i] * 8,
+                                                  base + offC[i * n + j] + (size_t)c0 * ldc8 * 8, (size_t)ldc8 * 8, (size_t)row_len[i] * 8,
+                                                  c1 - c0, cudaMemcpyDeviceToHost, ctx->d2h_stream);
+                    }
+                }
             }
             if (e != cudaSuccess || rc != MB_OK) break;
+            const bool chunked_out = (i == m - 1 && j == n - 1 && col_len[j] >= 1024);
+            if (chunked_out) continue;               // already downloaded chunk by chunk
             e = cudaEventCreateWithFlags(&evC[i * n + j], cudaEventDisableTiming);
             if (e == cudaSuccess) e = cudaEventRecord(evC[i * n + j], ctx->stream);
             if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->d2h_stream, evC[i * n + j], 0);
@@ -709,6 +762,7 @@ int32_t mb_matmul_blocked_host(mb_ctx* ctx, const double* const* A_host, const d
     for (auto ev : evA) if (ev) cudaEventDestroy(ev);
     for (auto ev : evB) if (ev) cudaEventDestroy(ev);
     for (auto ev : evC) if (ev) cudaEventDestroy(ev);
+    for (auto ev : chunk_events) if (ev) cudaEventDestroy(ev);
     if (ev_start) cudaEventDestroy(ev_start);
     if (ev_done) cudaEventDestroy(ev_done);
     if (rc != MB_OK) return rc;

@@ -334,15 +334,17 @@ def test_matmul_blocked_seq_order(gpu, oracle):
             assert np.abs(got - refb[(i, j)]).max() <= 1e-12
 
 
-def test_matmul_blocked_host_pipelined(gpu, oracle):
-    """mb_matmul_blocked_host: host tiles in, host tiles out (pipelined H2D / DMMA / D2H) == BlockMatrix.multiply."""
+@pytest.mark.parametrize("dims", [(75, 64, 51, 2, 3, 2), (300, 200, 2100, 1, 2, 2), (260, 130, 1100, 1, 1, 1)])
+def test_matmul_blocked_host_pipelined(gpu, oracle, dims):
+    """mb_matmul_blocked_host: host tiles in, host tiles out (pipelined H2D / DMMA / D2H) == BlockMatrix.multiply.
+    Column counts >= 1024 exercise the chunked first product (B uploaded in quarters) and chunked last download."""
     lib, ctx = gpu
     rng = np.random.default_rng(12)
-    M, K, N, m, k, n = 75, 64, 51, 2, 3, 2
+    M, K, N, m, k, n = dims
     A, B = rng.random((M, K)) - 0.5, rng.random((K, N)) - 0.5
     oa = oracle.DenseVecMatrix(list(enumerate(A))).to_block_matrix(m, k)
     ob = oracle.DenseVecMatrix(list(enumerate(B))).to_block_matrix(k, n)
-    ref = dict(oa.multiply(ob, gemm="f2j").blocks)
+    ref = dict(oa.multiply(ob, gemm="blas" if N > 1000 else "f2j").blocks)
     ta, tb = dict(oa.blocks), dict(ob.blocks)
     a_arr = [np.asfortranarray(ta[(i, kk)]) for i in range(m) for kk in range(k)]
     b_arr = [np.asfortranarray(tb[(kk, j)]) for kk in range(k) for j in range(n)]
