@@ -281,8 +281,7 @@ __global__ void convert_strided_kernel(int rows, int cols, const TI* a, long lon
 // ---- XORShift uniform generator (utils/RandomDataGenerator.scala:113-131) ----
 // state' = s ^ (s<<21); ^= (>>>35); ^= (<<4).  The map is GF(2)-linear, so value i of a partition
 // stream is reachable by a jump: state_i = T^(2i) * state_0 (nextDouble consumes two steps).
-// jump[j] holds the 64 columns of T^(2^j); a chunk start is the product of the set bits of 2*first.
-__constant__ unsigned long long c_jump[40][64];
+// g_jump[j] holds the 64 columns of T^(2^j); a chunk start is the product of the set bits of 2*first.
 
 __device__ __forceinline__ unsigned long long xs_step(unsigned long long s) {
     s ^= s << 21;
@@ -290,25 +289,6 @@ __device__ __forceinline__ unsigned long long xs_step(unsigned long long s) {
     s ^= s << 4;
     return s;
 }
-__device__ unsigned long long xs_jump(unsigned long long s, unsigned long long steps) {
-    for (int j = 0; j < 40 && steps; ++j, steps >>= 1) {
-        if (steps & 1ull) {
-            unsigned long long t = 0;
-            unsigned long long x = s;
-            // t = sum over set bits b of x of column b
-            while (x) {
-                const int b = __ffsll((long long)x) - 1;
-                t ^= c_jump[j][b];
-                x &= x - 1;
-            }
-            s = t;
-        }
-    }
-    return s;
-}
-// Block = 256 threads, thread t generates FILL_CHUNK consecutive values of the stream into shared memory, then the
-// block writes its 8192 values with coalesced stores.  The jump is hierarchical: every thread applies the block's
-// base offset (shared bits of the step count) plus its own t*2*FILL_CHUNK steps.
 constexpr int FILL_CHUNK = 16;   // values per thread (256 x 17 x 8 B = 34 KiB of static smem)
 __device__ unsigned long long g_jump[40][64];      // same tables in global memory: lane-parallel (coalesced) access
 
@@ -540,8 +520,7 @@ cudaError_t fill_uniform_init_tables() {
         }
         built = true;
     }
-    cudaError_t e = cudaMemcpyToSymbol(c_jump, tab, sizeof(tab));
-    if (e == cudaSuccess) e = cudaMemcpyToSymbol(g_jump, tab, sizeof(tab));
+    cudaError_t e = cudaMemcpyToSymbol(g_jump, tab, sizeof(tab));
     if (e == cudaSuccess && dev >= 0 && dev < 64) done[dev] = true;
     return e;
 }
