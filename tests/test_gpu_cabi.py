@@ -360,3 +360,24 @@ def test_matmul_blocked_host_pipelined(gpu, oracle, dims):
         for i in range(m):
             for j in range(n):
                 assert np.abs(c_arr[i * n + j] - ref[(i, j)]).max() <= 1e-12
+
+
+def test_dgemm_degenerate_cases(gpu):
+    """netlib dgemm corner cases: k = 0 and alpha = 0 reduce to C := beta*C (dgemm.f quick returns), m or n = 0 is a no-op,
+    bad arguments are rejected like xerbla."""
+    import torch
+    lib, ctx = gpu
+    p = lambda t: C.c_void_p(t.data_ptr())
+    Cm = torch.arange(12, dtype=torch.float64, device="cuda").reshape(3, 4).contiguous()      # column-major 4 x 3
+    A = torch.ones(8, dtype=torch.float64, device="cuda")
+    ref = Cm.clone()
+    nat.check(lib.mb_dgemm_device(ctx, b"N", b"N", 4, 3, 0, 1.0, p(A), 4, p(A), 1, 2.0, p(Cm), 4))
+    nat.check(lib.mb_synchronize(ctx))
+    assert torch.equal(Cm, 2.0 * ref)
+    nat.check(lib.mb_dgemm_device(ctx, b"N", b"N", 4, 3, 2, 0.0, p(A), 4, p(A), 2, 0.0, p(Cm), 4))
+    nat.check(lib.mb_synchronize(ctx))
+    assert torch.equal(Cm, torch.zeros_like(Cm))
+    assert lib.mb_dgemm_device(ctx, b"N", b"N", 0, 3, 2, 1.0, p(A), 1, p(A), 2, 0.0, p(Cm), 1) == nat.MB_OK
+    assert lib.mb_dgemm_device(ctx, b"X", b"N", 4, 3, 2, 1.0, p(A), 4, p(A), 2, 0.0, p(Cm), 4) == nat.MB_ERR_INVALID_ARG
+    assert lib.mb_dgemm_device(ctx, b"N", b"N", 4, 3, 2, 1.0, p(A), 3, p(A), 2, 0.0, p(Cm), 4) == nat.MB_ERR_INVALID_ARG   # lda < m
+    assert lib.mb_dgemm_device(ctx, b"N", b"N", -1, 3, 2, 1.0, p(A), 4, p(A), 2, 0.0, p(Cm), 4) == nat.MB_ERR_INVALID_ARG
