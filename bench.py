@@ -250,11 +250,14 @@ def run_ours(args):
         flops_per_launch = local_products * 2.0 * bs ** 3 / launches_per_step
     gemm_avg_ms = gemm_ms / max(1, gemm_n)
     achieved = flops_per_launch / (gemm_avg_ms * 1e-3) / 1e12 if gemm_n else None
+    # DRAM traffic of that launch: ncu (--set full) measured dram read+write of ONE 8192^3 block product
+    # (profiles/r01_ncu_gemm_f64_dmma.md); a launch that covers several products is scaled by their count.
     traffic = None
     summary = ROOT / "profiles" / "ncu_summary.json"
-    if summary.exists():
+    if summary.exists() and not tall and (N, g) == (16384, 2):
         try:
-            traffic = json.loads(summary.read_text()).get("gemm_f64_dmma", {}).get("dram_bytes_per_launch")
+            per_product = json.loads(summary.read_text()).get("gemm_f64_dmma", {}).get("dram_bytes_per_launch")
+            traffic = per_product * local_products / launches_per_step if per_product else None
         except Exception:
             traffic = None
     peak, peak_src = FP64_PEAK_TFLOPS_MEASURED, None
