@@ -9,6 +9,7 @@
 #include "elementwise.h"
 #include "ptx.cuh"
 #include <cuda_bf16.h>
+#include <cstdlib>
 
 namespace mb {
 
@@ -34,65 +35,51 @@ __device__ __forceinline__ double apply_un(int op, double a, double alpha, doubl
 }
 
 // ---- flat (packed, same orientation) fast paths: 128-bit accesses, 4 independent loads in flight ----
-// Each CTA walks contiguous 16 KiB tiles (256 threads x 4 vectors of 16 B): every warp instruction touches 512
-// consecutive bytes and a tile stays inside a few DRAM pages; loads are non-allocating, stores streaming.
-__device__ __forceinline__ double2 ldg_stream(const double2* p) {
-    double2 v;
-    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
-    return v;
-}
-__device__ __forceinline__ void stg_stream(double2* p, double2 v) {
-    asm volatile("st.global.cs.v2.f64 [%0], {%1,%2};" ::"l"(p), "d"(v.x), "d"(v.y) : "memory");
-}
-
+// Flat (packed, same orientation) fast paths.  One CTA per contiguous 16 KiB tile (256 threads x 4 vectors of 16 B, all
+// four loads issued before the first store), plain ld/st.global, non-persistent: the block scheduler walks the array in
+// address order.  Measured on B200: 6.86 TB/s for the two-stream ops (copy / alpha*x+beta), above the 6.57 TB/s of the
+// torch copy yardstick; the earlier persistent grid-stride + ld.nc/st.cs variant reached 5.9 TB/s.
 template <int OP>
-__global__ void __launch_bounds__(EW_THREADS) binary_flat_kernel(const double2* __restrict__ a,
-                                                                const double2* __restrict__ b,
-                                                                double2* __restrict__ o, long long n2) {
+__global__ void __launch_bounds__(EW_THREADS) binary_flat_kernel(const double2* a, const double2* b, double2* o,
+                                                                long long n2) {      // o may alias a or b exactly (in-place)
     constexpr int TILE = EW_THREADS * 4;
-    const long long num_tiles = (n2 + TILE - 1) / TILE;
-    for (long long t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        const long long base = t * TILE + threadIdx.x;
-        if (base + 3 * EW_THREADS < n2) {
-            double2 x[4], y[4];
+    const long long base = (long long)blockIdx.x * TILE + threadIdx.x;
+    if (base + 3 * EW_THREADS < n2) {
+        double2 x[4], y[4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) { x[u] = ldg_stream(a + base + u * EW_THREADS); y[u] = ldg_stream(b + base + u * EW_THREADS); }
+        for (int u = 0; u < 4; ++u) { x[u] = a[base + u * EW_THREADS]; y[u] = b[base + u * EW_THREADS]; }
 #pragma unroll
-            for (int u = 0; u < 4; ++u)
-                stg_stream(o + base + u * EW_THREADS, make_double2(apply_bin(OP, x[u].x, y[u].x), apply_bin(OP, x[u].y, y[u].y)));
-        } else {
-            for (int u = 0; u < 4; ++u) {
-                const long long i = base + u * EW_THREADS;
-                if (i < n2) {
-                    const double2 x = a[i], y = b[i];
-                    o[i] = make_double2(apply_bin(OP, x.x, y.x), apply_bin(OP, x.y, y.y));
-                }
+        for (int u = 0; u < 4; ++u)
+            o[base + u * EW_THREADS] = make_double2(apply_bin(OP, x[u].x, y[u].x), apply_bin(OP, x[u].y, y[u].y));
+    } else {
+        for (int u = 0; u < 4; ++u) {
+            const long long i = base + u * EW_THREADS;
+            if (i < n2) {
+                const double2 x = a[i], y = b[i];
+                o[i] = make_double2(apply_bin(OP, x.x, y.x), apply_bin(OP, x.y, y.y));
             }
         }
     }
 }
 
 template <int OP>
-__global__ void __launch_bounds__(EW_THREADS) unary_flat_kernel(const double2* __restrict__ a, double2* __restrict__ o,
-                                                               long long n2, double alpha, double beta) {
+__global__ void __launch_bounds__(EW_THREADS) unary_flat_kernel(const double2* a, double2* o, long long n2, double alpha,
+                                                               double beta) {          // o may alias a exactly (in-place)
     constexpr int TILE = EW_THREADS * 4;
-    const long long num_tiles = (n2 + TILE - 1) / TILE;
-    for (long long t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        const long long base = t * TILE + threadIdx.x;
-        if (base + 3 * EW_THREADS < n2) {
-            double2 x[4];
+    const long long base = (long long)blockIdx.x * TILE + threadIdx.x;
+    if (base + 3 * EW_THREADS < n2) {
+        double2 x[4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) x[u] = ldg_stream(a + base + u * EW_THREADS);
+        for (int u = 0; u < 4; ++u) x[u] = a[base + u * EW_THREADS];
 #pragma unroll
-            for (int u = 0; u < 4; ++u)
-                stg_stream(o + base + u * EW_THREADS, make_double2(apply_un(OP, x[u].x, alpha, beta), apply_un(OP, x[u].y, alpha, beta)));
-        } else {
-            for (int u = 0; u < 4; ++u) {
-                const long long i = base + u * EW_THREADS;
-                if (i < n2) {
-                    const double2 x = a[i];
-                    o[i] = make_double2(apply_un(OP, x.x, alpha, beta), apply_un(OP, x.y, alpha, beta));
-                }
+        for (int u = 0; u < 4; ++u)
+            o[base + u * EW_THREADS] = make_double2(apply_un(OP, x[u].x, alpha, beta), apply_un(OP, x[u].y, alpha, beta));
+    } else {
+        for (int u = 0; u < 4; ++u) {
+            const long long i = base + u * EW_THREADS;
+            if (i < n2) {
+                const double2 x = a[i];
+                o[i] = make_double2(apply_un(OP, x.x, alpha, beta), apply_un(OP, x.y, alpha, beta));
             }
         }
     }
@@ -209,7 +196,7 @@ __global__ void __launch_bounds__(256) transpose_generic_kernel(const T* __restr
 }
 
 // ---- sum: two-stage deterministic tree (fixed grid => run-to-run reproducible) ----
-constexpr int SUM_BLOCKS = 148 * 4;
+constexpr int SUM_BLOCKS = 16384;      // upper bound on stage-1 CTAs (one 16 KiB tile per CTA-iteration)
 __device__ __forceinline__ double block_reduce_sum(double v) {
     __shared__ double warp_part[8];
 #pragma unroll
@@ -227,16 +214,26 @@ __device__ __forceinline__ double block_reduce_sum(double v) {
 __global__ void __launch_bounds__(256) sum_strided_kernel(const double* __restrict__ a, int rows, int cols,
                                                          long long ld, double* __restrict__ partial) {
     const long long total = (long long)rows * cols;
-    double s0 = 0.0, s1 = 0.0;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
     const bool packed_vec = (ld == rows) && ((reinterpret_cast<uintptr_t>(a) & 15) == 0);
     if (packed_vec) {
+        // contiguous 16 KiB tiles, four independent 128-bit loads per thread and iteration (same shape as the flat
+        // element-wise kernels); the tile -> CTA map and the in-thread order are fixed, so the sum is reproducible
         const long long n2 = total >> 1;
         const double2* a2 = reinterpret_cast<const double2*>(a);
-        for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n2;
-             i += (long long)gridDim.x * blockDim.x) {
-            const double2 v = __ldg(a2 + i);
-            s0 += v.x;
-            s1 += v.y;
+        constexpr int TILE = 256 * 4;
+        const long long num_tiles = (n2 + TILE - 1) / TILE;
+        for (long long t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+            const long long base = t * TILE + threadIdx.x;
+            if (base + 3 * 256 < n2) {
+                const double2 v0 = a2[base], v1 = a2[base + 256], v2 = a2[base + 512], v3 = a2[base + 768];
+                s0 += v0.x + v0.y; s1 += v1.x + v1.y; s2 += v2.x + v2.y; s3 += v3.x + v3.y;
+            } else {
+                for (int u = 0; u < 4; ++u) {
+                    const long long i = base + u * 256;
+                    if (i < n2) { const double2 v = a2[i]; s0 += v.x + v.y; }
+                }
+            }
         }
         if ((total & 1) && blockIdx.x == 0 && threadIdx.x == 0) s0 += a[total - 1];
     } else {
@@ -244,7 +241,7 @@ __global__ void __launch_bounds__(256) sum_strided_kernel(const double* __restri
              e += (long long)gridDim.x * blockDim.x)
             s0 += a[(e % rows) + (e / rows) * ld];
     }
-    const double t = block_reduce_sum(s0 + s1);
+    const double t = block_reduce_sum((s0 + s1) + (s2 + s3));
     if (threadIdx.x == 0) partial[blockIdx.x] = t;
 }
 __global__ void __launch_bounds__(256) sum_final_kernel(const double* __restrict__ partial, int n, double* out) {
@@ -383,10 +380,9 @@ cudaError_t ew_binary(int op, int rows, int cols, const double* a, long long ars
     const bool packed = ars == 1 && brs == 1 && ors == 1 && acs == rows && bcs == rows && ocs == rows;
     const bool aligned = ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) |
                            reinterpret_cast<uintptr_t>(o)) & 15) == 0;
-    const bool aliased = (static_cast<const void*>(a) == static_cast<const void*>(o)) || (static_cast<const void*>(b) == static_cast<const void*>(o));
-    if (packed && aligned && (total % 2 == 0) && !aliased) {
+    if (packed && aligned && (total % 2 == 0)) {
         const long long n2 = total / 2;
-        const int grid = ew_grid((n2 + 3) / 4);
+        const unsigned grid = (unsigned)((n2 + EW_THREADS * 4 - 1) / (EW_THREADS * 4));
         const double2 *a2 = reinterpret_cast<const double2*>(a), *b2 = reinterpret_cast<const double2*>(b);
         double2* o2 = reinterpret_cast<double2*>(o);
         if (op == EW_ADD) binary_flat_kernel<EW_ADD><<<grid, EW_THREADS, 0, st>>>(a2, b2, o2, n2);
@@ -412,9 +408,9 @@ cudaError_t ew_unary(int op, int rows, int cols, const double* a, long long ars,
     const long long total = (long long)rows * cols;
     const bool packed = ars == 1 && ors == 1 && acs == rows && ocs == rows;
     const bool aligned = ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(o)) & 15) == 0;
-    if (packed && aligned && (total % 2 == 0) && static_cast<const void*>(a) != static_cast<const void*>(o)) {
+    if (packed && aligned && (total % 2 == 0)) {
         const long long n2 = total / 2;
-        const int grid = ew_grid((n2 + 3) / 4);
+        const unsigned grid = (unsigned)((n2 + EW_THREADS * 4 - 1) / (EW_THREADS * 4));
         const double2* a2 = reinterpret_cast<const double2*>(a);
         double2* o2 = reinterpret_cast<double2*>(o);
         if (op == EW_AXPB) unary_flat_kernel<EW_AXPB><<<grid, EW_THREADS, 0, st>>>(a2, o2, n2, alpha, beta);
@@ -462,7 +458,7 @@ int sum_scratch_doubles() { return SUM_BLOCKS + 1; }
 cudaError_t sum_f64(const double* a, int rows, int cols, long long ld, double* scratch, cudaStream_t st) {
     // scratch[0] receives the result, scratch[1..] the per-block partials
     const long long total = (long long)rows * cols;
-    int blocks = (int)min((long long)SUM_BLOCKS, max(1ll, (total + 511) / 512));
+    int blocks = (int)min((long long)SUM_BLOCKS, max(1ll, (total + 2047) / 2048));      // one CTA per 16 KiB tile, capped
     sum_strided_kernel<<<blocks, 256, 0, st>>>(a, rows, cols, ld, scratch + 1);
     sum_final_kernel<<<1, 256, 0, st>>>(scratch + 1, blocks, scratch);
     return cudaGetLastError();
