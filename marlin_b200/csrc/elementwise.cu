@@ -134,12 +134,27 @@ __global__ void binary_strided_f32_kernel(int op, int rows, int cols, const floa
 // Shared-memory slot of 16B unit (rb, cb, half):  rb*64 + 16*(cb>>3) + 8*half + ((cb&7) ^ (rb&7))
 // which is conflict-free for the column-wise writes and the row-wise reads.
 constexpr int TT = 64;
+// Tiles are visited in 8 x 8 super-tiles (1-D grid, super-tile-major): the CTAs resident at any moment read 4 KiB runs
+// of 8 adjacent tiles per input column and write 4 KiB runs per output column, instead of 512 B pieces 128 KiB apart.
+template <bool SUPER>
 __global__ void __launch_bounds__(256) transpose_f64_tile_kernel(const double* __restrict__ in, long long ldi,
                                                                 double* __restrict__ out, long long ldo, int rows,
-                                                                int cols) {
+                                                                int cols, int tiles_r, int tiles_c) {
     __shared__ double2 tile[32 * 64];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int r0 = blockIdx.x * TT, c0 = blockIdx.y * TT;
+    int tr, tc;
+    if (SUPER) {
+        const int sup_r = (tiles_r + 7) >> 3;
+        const int b = blockIdx.x;
+        const int sup = b >> 6, inner = b & 63;
+        tr = ((sup % sup_r) << 3) + (inner & 7);
+        tc = ((sup / sup_r) << 3) + (inner >> 3);
+        if (tr >= tiles_r || tc >= tiles_c) return;
+    } else {
+        tr = blockIdx.x % tiles_r;
+        tc = blockIdx.x / tiles_r;
+    }
+    const int r0 = tr * TT, c0 = tc * TT;
     // load phase: lane -> micro-row rb, warp -> micro-cols cb = warp + 8*i
     {
         const int rb = lane;
@@ -150,8 +165,8 @@ __global__ void __launch_bounds__(256) transpose_f64_tile_kernel(const double* _
             const int c = c0 + 2 * cb;
             double2 v0 = make_double2(0.0, 0.0), v1 = v0;
             if (r < rows && c < cols) {   // rows, cols even -> whole micro-block in range
-                v0 = __ldg(reinterpret_cast<const double2*>(in + r + (long long)c * ldi));
-                v1 = __ldg(reinterpret_cast<const double2*>(in + r + (long long)(c + 1) * ldi));
+                v0 = *reinterpret_cast<const double2*>(in + r + (long long)c * ldi);
+                v1 = *reinterpret_cast<const double2*>(in + r + (long long)(c + 1) * ldi);
             }
             const int base = rb * 64 + 16 * (cb >> 3) + ((cb & 7) ^ (rb & 7));
             tile[base] = make_double2(v0.x, v1.x);       // out column r   : in(r, c), in(r, c+1)
@@ -429,8 +444,15 @@ cudaError_t transpose_f64(const double* in, long long ldi, double* out, long lon
     const bool fast = (rows % 2 == 0) && (cols % 2 == 0) && (ldi % 2 == 0) && (ldo % 2 == 0) &&
                       (((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) == 0);
     if (fast) {
-        dim3 grid((rows + TT - 1) / TT, (cols + TT - 1) / TT);
-        transpose_f64_tile_kernel<<<grid, 256, 0, st>>>(in, ldi, out, ldo, rows, cols);
+        const int tiles_r = (rows + TT - 1) / TT, tiles_c = (cols + TT - 1) / TT;
+        static int variant = -1;
+        if (variant < 0) { const char* ev = getenv("MARLIN_B200_TRANSPOSE_VARIANT"); variant = ev ? atoi(ev) : 0; }   // measured: the super-tile order (1) is ~1.5 % slower than the plain order (0)
+        if (variant == 1) {
+            const int sup = ((tiles_r + 7) / 8) * ((tiles_c + 7) / 8);
+            transpose_f64_tile_kernel<true><<<sup * 64, 256, 0, st>>>(in, ldi, out, ldo, rows, cols, tiles_r, tiles_c);
+        } else {
+            transpose_f64_tile_kernel<false><<<tiles_r * tiles_c, 256, 0, st>>>(in, ldi, out, ldo, rows, cols, tiles_r, tiles_c);
+        }
     } else {
         dim3 grid((rows + 31) / 32, (cols + 31) / 32);
         transpose_generic_kernel<double><<<grid, 256, 0, st>>>(in, ldi, out, ldo, rows, cols);

@@ -1,10 +1,10 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-timeout 200 python scripts/bench_kernels.py > gpurun_out/kernels.log 2>&1; python - <<'PY'
+timeout 300 python -m pytest tests/test_gpu_cabi.py -x -q -k "transpose or elementwise or sum" 2>&1 | tail -2
+for v in 0 1; do MARLIN_B200_TRANSPOSE_VARIANT=$v timeout 200 python scripts/bench_kernels.py > gpurun_out/kernels_v$v.log 2>&1; python - <<'PY'
 import json
 d=json.load(open('gpurun_out/kernels.json'))
 for size,res in d['hbm_kernels'].items():
-    print(size, {k.split(' ')[0]: round(v['GB/s']) for k,v in res.items()})
+    print(size, {k.split(' ')[0]: round(v['GB/s']) for k,v in res.items() if k.startswith('transpose')})
 PY
-timeout 300 ncu --set full --clock-control none -k regex:"binary_flat|unary_flat|transpose_f64|sum_strided" -s 5 -c 5 -o gpurun_out/prof_hbm -f python scripts/ncu_hbm.py > gpurun_out/ncu_hbm.log 2>&1; tail -1 gpurun_out/ncu_hbm.log
+done
