@@ -123,6 +123,8 @@ int32_t mb_block_sub(mb_ctx* ctx, const mb_block* A, const mb_block* B, mb_block
 int32_t mb_block_hadamard(mb_ctx* ctx, const mb_block* A, const mb_block* B, mb_block* out); /* A :* B (BlockMatrix.scala:494-500) */
 /* out = alpha*A + beta  (add(b): alpha=1; multiply(b): beta=0; subtractBy(b): alpha=-1, beta=b) */
 int32_t mb_block_axpb(mb_ctx* ctx, const mb_block* A, double alpha, double beta, mb_block* out);
+/* BDM.zeros / BDM.fill: every element of the (possibly strided) block := value */
+int32_t mb_block_fill(mb_ctx* ctx, mb_block* blk, double value);
 /* out = A / b  (true IEEE division, SubMatrix.divide) and out = b / A (divideBy) */
 int32_t mb_block_div(mb_ctx* ctx, const mb_block* A, double b, int32_t b_over_a, mb_block* out);
 /* ---- a9: BlockMatrix.transpose -> denseBlock.t.copy (matrix/BlockMatrix.scala:514-523) -- */

@@ -62,6 +62,7 @@ SIGNATURES = {
     "mb_block_sub": (c_i32, [c_ctx, c_blk, c_blk, c_blk]),
     "mb_block_hadamard": (c_i32, [c_ctx, c_blk, c_blk, c_blk]),
     "mb_block_axpb": (c_i32, [c_ctx, c_blk, c_f64, c_f64, c_blk]),
+    "mb_block_fill": (c_i32, [c_ctx, c_blk, c_f64]),
     "mb_block_div": (c_i32, [c_ctx, c_blk, c_f64, c_i32, c_blk]),
     "mb_block_transpose": (c_i32, [c_ctx, c_blk, c_blk]),
     "mb_block_copy": (c_i32, [c_ctx, c_blk, c_blk]),

@@ -834,6 +834,9 @@ int32_t mb_block_hadamard(mb_ctx* ctx, const mb_block* A, const mb_block* B, mb_
 int32_t mb_block_axpb(mb_ctx* ctx, const mb_block* A, double alpha, double beta, mb_block* out) {
     return unary_op(ctx, mb::EW_AXPB, A, out, alpha, beta, "axpb");
 }
+int32_t mb_block_fill(mb_ctx* ctx, mb_block* blk, double value) {
+    return unary_op(ctx, mb::EW_FILL, blk, blk, 0.0, value, "fill");
+}
 int32_t mb_block_div(mb_ctx* ctx, const mb_block* A, double b, int32_t b_over_a, mb_block* out) {
     return unary_op(ctx, b_over_a ? mb::EW_RDIV : mb::EW_DIV, A, out, b, 0.0, "divide");
 }

@@ -30,6 +30,7 @@ __device__ __forceinline__ double apply_un(int op, double a, double alpha, doubl
         case EW_AXPB: return __dadd_rn(__dmul_rn(alpha, a), beta);
         case EW_DIV: return __ddiv_rn(a, alpha);
         case EW_RDIV: return __ddiv_rn(alpha, a);
+        case EW_FILL: return beta;
         default: return a;
     }
 }
@@ -109,6 +110,7 @@ __global__ void unary_strided_kernel(int op, int rows, int cols, const double* a
         if (op == EW_AXPB) v = __dadd_rn(__dmul_rn(alpha, x), beta);
         else if (op == EW_DIV) v = __ddiv_rn(x, alpha);
         else if (op == EW_RDIV) v = __ddiv_rn(alpha, x);
+        else if (op == EW_FILL) v = beta;
         else v = x;
         o[r * ors + c * ocs] = v;
     }
@@ -431,6 +433,7 @@ cudaError_t ew_unary(int op, int rows, int cols, const double* a, long long ars,
         if (op == EW_AXPB) unary_flat_kernel<EW_AXPB><<<grid, EW_THREADS, 0, st>>>(a2, o2, n2, alpha, beta);
         else if (op == EW_DIV) unary_flat_kernel<EW_DIV><<<grid, EW_THREADS, 0, st>>>(a2, o2, n2, alpha, beta);
         else if (op == EW_RDIV) unary_flat_kernel<EW_RDIV><<<grid, EW_THREADS, 0, st>>>(a2, o2, n2, alpha, beta);
+        else if (op == EW_FILL) unary_flat_kernel<EW_FILL><<<grid, EW_THREADS, 0, st>>>(a2, o2, n2, alpha, beta);
         else unary_flat_kernel<EW_COPY><<<grid, EW_THREADS, 0, st>>>(a2, o2, n2, alpha, beta);
     } else {
         unary_strided_kernel<<<ew_grid(total), EW_THREADS, 0, st>>>(op, rows, cols, a, ars, acs, o, ors, ocs, alpha, beta);

@@ -4,7 +4,7 @@
 namespace mb {
 
 enum { EW_ADD = 0, EW_SUB = 1, EW_MUL = 2 };               // binary ops
-enum { EW_AXPB = 10, EW_DIV = 11, EW_RDIV = 12, EW_COPY = 13 };   // unary ops
+enum { EW_AXPB = 10, EW_DIV = 11, EW_RDIV = 12, EW_COPY = 13, EW_FILL = 14 };   // unary ops (EW_FILL: out = beta)
 
 // A view's element (r,c) lives at base[r*rs + c*cs]  (col-major: rs=1, cs=ld; transposed view: rs=ld, cs=1).
 cudaError_t ew_binary(int op, int rows, int cols, const double* a, long long ars, long long acs, const double* b,
