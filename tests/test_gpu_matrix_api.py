@@ -251,3 +251,14 @@ def test_multiply_by_local_matrix(M):
     res = small.multiply(wide, 2, 1)                   # broadcastThreshold = 1 MB: B too big to broadcast, A small
     assert isinstance(res, M.BlockMatrix)
     assert np.array_equal(res.toBreeze(), Bl @ Xw)
+
+
+def test_example_drivers(M, capsys):
+    """The reference's multiply drivers (examples/MatrixMultiply, BLAS3, RMMcompare) with their own command lines."""
+    from marlin_b200.examples import BLAS3, MatrixMultiply, RMMcompare
+    MatrixMultiply.main(["300", "200", "100", "8"])
+    BLAS3.main(["256", "128", "64", "2", "2"])
+    BLAS3.main(["256", "128", "64", "3", "2", "2", "2"])
+    RMMcompare.main(["256", "256", "256", "2", "2", "2", "2"])
+    out = capsys.readouterr().out
+    assert "Result RDD counts" in out and "mode 3 used time" in out and "RMMv2 in mode 2 used time" in out
