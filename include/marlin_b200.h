@@ -134,6 +134,18 @@ int32_t mb_block_copy(mb_ctx* ctx, const mb_block* A, mb_block* out);
 /* BlockMatrix.sum per block (matrix/BlockMatrix.scala:467-472) */
 int32_t mb_block_sum(mb_ctx* ctx, const mb_block* A, double* sum_out);
 
+/* ---- vector side of the path: a vector is a block with one column (or one row) ----
+ * y = A x (+ y): SubMatrix.multiply(v: Vector) (matrix/SubMatrix.scala:131-139) -> Breeze `BDM * BDV` -> netlib dgemv;
+ * used per block by BlockMatrix.multiply(v: DistributedVector / BDV) (matrix/BlockMatrix.scala:240-274), whose
+ * reduceByKey sum is `accumulate`.  A may be a transposed view (row-major rows of a DenseVecMatrix,
+ * matrix/DenseVecMatrix.scala:178-191).  Reads A once: 8*rows*cols bytes. */
+int32_t mb_block_gemv(mb_ctx* ctx, const mb_block* A, const mb_block* x, mb_block* y, int32_t accumulate);
+/* x^T y: DistributedVector.multiply, row x column case (matrix/DistributedVector.scala:164-176) -> Breeze `v.t * w`. */
+int32_t mb_block_dot(mb_ctx* ctx, const mb_block* x, const mb_block* y, double* dot_out);
+/* out = x y^T: DistributedVector.multiply, column x row case (matrix/DistributedVector.scala:149-161)
+ * -> Breeze `v * w.t` -> dgemm with k = 1. */
+int32_t mb_block_ger(mb_ctx* ctx, const mb_block* x, const mb_block* y, mb_block* out);
+
 /* ---- a11: MTUtils.randomDenVecMatrix / randomBlockMatrix input generation
  *      (utils/MTUtils.scala:34-73, rdd/RandomRDD.scala:28-101, utils/RandomDataGenerator.scala:53-65,113-131).
  * Fills `count` consecutive values of partition stream `partition_seed` (one XORShift stream per

@@ -1,14 +1,14 @@
 """marlin_b200 — B200-native engine for the dense block-matrix hot path of PasaLab/marlin.
 
 Public surface mirrors edu.nju.pasalab.marlin.{matrix,utils,rdd} for that path only:
-BlockMatrix / DenseVecMatrix / SubMatrix / BlockID, MTUtils, MatrixMultPartitioner /
+BlockMatrix / DenseVecMatrix / DistributedVector / SubMatrix / BlockID, MTUtils, MatrixMultPartitioner /
 MatrixElemOpPartitioner.  All arithmetic runs in libmarlin_b200.so (hand-written sm_100a kernels).
 """
 from ._native import MarlinArgumentError, MarlinError
-from .matrix import BlockID, BlockMatrix, DenseVecMatrix, DistributedMatrix, SubMatrix
+from .matrix import BlockID, BlockMatrix, DenseVecMatrix, DistributedMatrix, DistributedVector, SubMatrix
 from .rdd import MatrixElemOpPartitioner, MatrixMultPartitioner
 from .runtime import Runtime
 from .utils import MTUtils
 
-__all__ = ["BlockID", "BlockMatrix", "DenseVecMatrix", "DistributedMatrix", "SubMatrix", "MTUtils",
+__all__ = ["BlockID", "BlockMatrix", "DenseVecMatrix", "DistributedMatrix", "DistributedVector", "SubMatrix", "MTUtils",
            "MatrixElemOpPartitioner", "MatrixMultPartitioner", "Runtime", "MarlinError", "MarlinArgumentError"]

@@ -6,8 +6,10 @@
 #include "gemm_f64.h"
 #include "gemm_bf16.h"
 #include "gemm_ozaki.h"
+#include "blas12.h"
 
 #include <cuda_runtime.h>
+#include <algorithm>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -34,6 +36,9 @@ struct mb_ctx {
     int fp64_bits = 7;
     void* ozaki_ws = nullptr;
     size_t ozaki_ws_bytes = 0;
+    // partial vectors of the matrix x vector kernels (grow-only)
+    double* vec_ws = nullptr;
+    size_t vec_ws_doubles = 0;
 };
 
 struct mb_block {
@@ -182,6 +187,22 @@ int32_t copy_convert(mb_ctx* ctx, const mb_block* A, mb_block* out) {
     return MB_OK;
 }
 
+
+// A block with one column (or one row) read as a vector: element i lives at p[i * inc].
+struct vec_view {
+    double* p;
+    long long inc;
+    int len;
+};
+bool as_vector(const mb_block* b, vec_view* v) {
+    if (b->dtype != MB_F64) return false;
+    if (b->cols == 1) { v->len = b->rows; v->inc = rs(b); }
+    else if (b->rows == 1) { v->len = b->cols; v->inc = cs(b); }
+    else return false;
+    v->p = f64_ptr(b);
+    return true;
+}
+
 }  // namespace
 
 extern "C" {
@@ -209,7 +230,7 @@ int32_t mb_init(int32_t device, mb_ctx** out) {
     ctx->num_sms = prop.multiProcessorCount;
     MB_CUDA(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
     ctx->stream = ctx->own_stream;
-    MB_CUDA(cudaMalloc(&ctx->scratch, sizeof(double) * mb::sum_scratch_doubles()));
+    MB_CUDA(cudaMalloc(&ctx->scratch, sizeof(double) * std::max(mb::sum_scratch_doubles(), mb::dot_scratch_doubles())));
     MB_CUDA(cudaMallocHost(&ctx->host_scalar, sizeof(double)));
     MB_CUDA(cudaEventCreate(&ctx->ev0));
     MB_CUDA(cudaEventCreate(&ctx->ev1));
@@ -222,6 +243,7 @@ int32_t mb_shutdown(mb_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     if (ctx->scratch) cudaFree(ctx->scratch);
+    if (ctx->vec_ws) cudaFree(ctx->vec_ws);
     if (ctx->host_scalar) cudaFreeHost(ctx->host_scalar);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
@@ -512,6 +534,16 @@ int32_t mb_block_gemm(mb_ctx* ctx, const mb_block* A, const mb_block* B, mb_bloc
         return fail(MB_ERR_DIM_MISMATCH, "mb_block_gemm: result block is %dx%d, expected %dx%d", C->rows, C->cols, A->rows, B->cols);
     const int M = A->rows, N = B->cols, K = A->cols;
     if (A->dtype == MB_F64 && B->dtype == MB_F64 && C->dtype == MB_F64) {
+        // degenerate shapes are HBM-bound vector kernels, not tensor-core tiles
+        if (N == 1 && M > 1) return mb_block_gemv(ctx, A, B, C, accumulate);                 // matrix x column
+        if (M == 1 && N > 1) {                                                              // row x matrix = (B^T a^T)^T
+            mb_block bt = *B;
+            bt.is_transpose = !B->is_transpose;
+            std::swap(bt.rows, bt.cols);
+            bt.owns = 0;
+            return mb_block_gemv(ctx, &bt, A, C, accumulate);
+        }
+        if (K == 1 && !accumulate && M > 1 && N > 1) return mb_block_ger(ctx, A, B, C);     // column x row
         if (!C->is_transpose) {
             return dgemm_device_impl(ctx, A->is_transpose ? 'T' : 'N', B->is_transpose ? 'T' : 'N', M, N, K, 1.0, f64_ptr(A),
                                      A->ld, f64_ptr(B), B->ld, accumulate ? 1.0 : 0.0, f64_ptr(C), C->ld, false);
@@ -872,6 +904,63 @@ int32_t mb_block_sum(mb_ctx* ctx, const mb_block* A, double* sum_out) {
     MB_CUDA(cudaMemcpyAsync(ctx->host_scalar, ctx->scratch, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     MB_CUDA(cudaStreamSynchronize(ctx->stream));
     *sum_out = *ctx->host_scalar;
+    return MB_OK;
+}
+
+int32_t mb_block_gemv(mb_ctx* ctx, const mb_block* A, const mb_block* x, mb_block* y, int32_t accumulate) {
+    MB_CTX(ctx);
+    if (!A || !x || !y) return fail(MB_ERR_INVALID_ARG, "mb_block_gemv: null block");
+    vec_view xv, yv;
+    if (A->dtype != MB_F64 || !as_vector(x, &xv) || !as_vector(y, &yv))
+        return fail(MB_ERR_UNSUPPORTED, "mb_block_gemv: fp64 matrix and fp64 single-column (or single-row) vectors only");
+    if (A->cols != xv.len)
+        return fail(MB_ERR_DIM_MISMATCH, "Dimension mismatch during matrix-vector multiplication: %d vs %d", A->cols, xv.len);
+    if (A->rows != yv.len)
+        return fail(MB_ERR_DIM_MISMATCH, "mb_block_gemv: result vector has %d elements, expected %d", yv.len, A->rows);
+    // a transposed view is the column-major (cols x rows) array underneath: y = S^T x
+    const bool trans = A->is_transpose != 0;
+    const int m = trans ? A->cols : A->rows, n = trans ? A->rows : A->cols;
+    const size_t need = mb::gemv_workspace_doubles(trans, m, n);
+    if (need > ctx->vec_ws_doubles) {
+        if (ctx->vec_ws) { MB_CUDA(cudaStreamSynchronize(ctx->stream)); MB_CUDA(cudaFree(ctx->vec_ws)); ctx->vec_ws = nullptr; ctx->vec_ws_doubles = 0; }
+        MB_CUDA(cudaMalloc(&ctx->vec_ws, need * sizeof(double)));
+        ctx->vec_ws_doubles = need;
+    }
+    int launches = 0;
+    MB_CUDA(mb::gemv_f64(trans, m, n, f64_ptr(A), A->ld, xv.p, xv.inc, yv.p, yv.inc, accumulate != 0, ctx->vec_ws, ctx->stream,
+                         &launches));
+    ctx->launches += launches;
+    return MB_OK;
+}
+
+int32_t mb_block_dot(mb_ctx* ctx, const mb_block* x, const mb_block* y, double* dot_out) {
+    MB_CTX(ctx);
+    if (!x || !y || !dot_out) return fail(MB_ERR_INVALID_ARG, "mb_block_dot: null argument");
+    vec_view xv, yv;
+    if (!as_vector(x, &xv) || !as_vector(y, &yv))
+        return fail(MB_ERR_UNSUPPORTED, "mb_block_dot: fp64 single-column (or single-row) vectors only");
+    if (xv.len != yv.len)
+        return fail(MB_ERR_DIM_MISMATCH, "the length of these two vectors are not the same: %d vs %d", xv.len, yv.len);
+    if (xv.len == 0) { *dot_out = 0.0; return MB_OK; }
+    MB_CUDA(mb::dot_f64(xv.len, xv.p, xv.inc, yv.p, yv.inc, ctx->scratch, ctx->stream));
+    ctx->launches += 2;
+    MB_CUDA(cudaMemcpyAsync(ctx->host_scalar, ctx->scratch, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    MB_CUDA(cudaStreamSynchronize(ctx->stream));
+    *dot_out = *ctx->host_scalar;
+    return MB_OK;
+}
+
+int32_t mb_block_ger(mb_ctx* ctx, const mb_block* x, const mb_block* y, mb_block* out) {
+    MB_CTX(ctx);
+    if (!x || !y || !out) return fail(MB_ERR_INVALID_ARG, "mb_block_ger: null block");
+    vec_view xv, yv;
+    if (out->dtype != MB_F64 || !as_vector(x, &xv) || !as_vector(y, &yv))
+        return fail(MB_ERR_UNSUPPORTED, "mb_block_ger: fp64 vectors and an fp64 result block only");
+    if (out->rows != xv.len || out->cols != yv.len)
+        return fail(MB_ERR_DIM_MISMATCH, "mb_block_ger: result block is %dx%d, expected %dx%d", out->rows, out->cols, xv.len, yv.len);
+    if (out->is_transpose) std::swap(xv, yv);       // (x y^T)^T = y x^T in the array underneath
+    MB_CUDA(mb::ger_f64(xv.len, yv.len, xv.p, xv.inc, yv.p, yv.inc, f64_ptr(out), out->ld, ctx->stream));
+    ctx->launches++;
     return MB_OK;
 }
 

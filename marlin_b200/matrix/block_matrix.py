@@ -107,10 +107,16 @@ class BlockMatrix(DistributedMatrix):
            multiply(other: DistributedMatrix, cores: Int, thr: Int = 300) :87
            multiply(other: DistributedMatrix, splitMode: (Int,Int,Int))   :131
            multiply(b: Double)                                            :229
-           multiply(B: BDM[Double])                                       :280"""
+           multiply(B: BDM[Double])                                       :280
+           multiply(v: DistributedVector) / multiply(v: BDV[Double])      :240 / :265"""
         from .dense_vec_matrix import DenseVecMatrix
+        from .distributed_vector import DistributedVector
         if isinstance(other, (int, float)) and not args:
             return self._scalar("multiply", float(other))
+        if isinstance(other, DistributedVector):
+            return self._multiply_dist_vector(other)                      # multiply(v: DistributedVector) :240
+        if isinstance(other, np.ndarray) and other.ndim == 1:
+            return self._multiply_vector(other)                           # multiply(v: BDV[Double]) :265
         if isinstance(other, np.ndarray) or isinstance(other, SubMatrix):
             return self._multiply_local(other)
         if args and isinstance(args[0], (tuple, list)):
@@ -511,6 +517,43 @@ class BlockMatrix(DistributedMatrix):
         # the reference reports numBlksByCol() although every key has column 0 (:301); kept
         return BlockMatrix(res, self.numRows(), b_cols, self.numBlksByRow(), self.numBlksByCol(),
                            placement=(lambda r, c, s=self: s.owner(r, 0)) if ws > 1 else None)
+
+    def _multiply_dist_vector(self, v):
+        """multiply(v: DistributedVector) :240-259 — piece `id` of v meets every block of block column `id`
+        (flatMap + join), block x piece on the GPU holding the block (mb_block_gemv), reduceByKey(add) over the block
+        row: a running accumulate for the blocks one rank holds, then partials to the rank of block (row, 0).
+        The result is labelled with v's length and split count, as the reference does (:252,257)."""
+        from .distributed_vector import DistributedVector
+        if self.numCols() != v.length:
+            raise nat.MarlinArgumentError(nat.MB_ERR_DIM_MISMATCH, "Dimension mismatch during matrix-matrix multiplication "
+                                          f"{self.numCols()} v.s {v.length}")
+        if self.numBlksByCol() != v.splitNum:
+            raise nat.MarlinArgumentError(nat.MB_ERR_UNSUPPORTED, "not supported matrix or vector")
+        pieces = v._replicated()
+        acc: Dict[int, SubMatrix] = {}
+        for b, blk in sorted(self.blocks, key=lambda t: (t[0].row, t[0].column)):
+            x = pieces[b.column]
+            if b.row in acc:
+                blk.multiply(x, out=acc[b.row], accumulate=True)
+            else:
+                acc[b.row] = blk.multiply(x)
+        rank, ws = world()
+        if ws > 1 and self.numBlksByCol() != 1:
+            acc = self._reduce_row_partials(acc)
+        return DistributedVector(sorted(acc.items()), v.length, v.splitNum, placement=lambda i, s=self: s.owner(i, 0))
+
+    def _multiply_vector(self, v: np.ndarray):
+        """multiply(v: BDV[Double]) :265-274 — broadcast vector, the matrix must not be split by column."""
+        from .distributed_vector import DistributedVector
+        v = np.asarray(v, dtype=np.float64).reshape(-1)
+        if self.numCols() != v.shape[0]:
+            raise nat.MarlinArgumentError(nat.MB_ERR_DIM_MISMATCH,
+                                          f"matrix columns size {self.numCols()} not support vector length {v.shape[0]}")
+        if self.numBlksByCol() != 1:
+            raise nat.MarlinArgumentError(nat.MB_ERR_UNSUPPORTED, "should not split the matrix by column")
+        x = SubMatrix(v.reshape(-1, 1))
+        res = [(b.row, blk.multiply(x)) for b, blk in sorted(self.blocks, key=lambda t: t[0].row)]
+        return DistributedVector(res, self.numRows(), self.numBlksByRow(), placement=lambda i, s=self: s.owner(i, 0))
 
     def multiplyBy(self, B) -> "BlockMatrix":
         """multiplyBy(B: BDM[Double]) :309-335 — a small local matrix times this block matrix (B replicated on every

@@ -106,8 +106,21 @@ class DenseVecMatrix(DistributedMatrix):
     def multiply(self, other, *args, **kwargs):
         """multiply(other, cores) :103; multiply(other, splitMode) :109; multiply(other, cores, thr) :196;
         multiply(B: BDM[Double]) :1660; multiply(b: Double) :853"""
+        from .distributed_vector import DistributedVector
         if isinstance(other, (int, float)) and not args:
             return self._scalar("multiply", float(other))
+        if isinstance(other, DistributedVector):
+            # multiply(vector: DistributedVector, splitMode: (Int, Int)) :149-154
+            mode = args[0] if args else kwargs["splitMode"]
+            if self.numCols() != other.length:
+                raise nat.MarlinArgumentError(nat.MB_ERR_DIM_MISMATCH, "Dimension mismatch during matrix-matrix multiplication: "
+                                              f"{self.numCols()} vs {other.length}")
+            return self.toBlockMatrix(int(mode[0]), int(mode[1])).multiply(other)
+        if isinstance(other, np.ndarray) and other.ndim == 1:
+            if args or "splitMode" in kwargs:
+                # multiply(vector: BDV[Double], splitMode: Int) :162-165
+                return self.toBlockMatrix(int(args[0] if args else kwargs["splitMode"]), 1).multiply(other)
+            return self._multiply_vector_local(other)                     # multiply(vector: BDV[Double]) :171-184
         if isinstance(other, (np.ndarray, SubMatrix)):
             return self._multiply_local(other)
         if args and isinstance(args[0], (tuple, list)):
@@ -157,6 +170,24 @@ class DenseVecMatrix(DistributedMatrix):
         res = self.toBlockMatrix(m, k).multiply(other.toBlockMatrix(k, n))
         # the reference labels the result grid (m, n) as requested (:134)
         return res
+
+    def _multiply_vector_local(self, vector: np.ndarray) -> np.ndarray:
+        """multiply(vector: BDV[Double]): BDV[Double] :171-184 — every row dotted with the broadcast vector, collected
+        into a local vector indexed by row id.  One gemv over the row-major shard (each row read once)."""
+        vector = np.asarray(vector, dtype=np.float64).reshape(-1)
+        parts = []
+        if self.data is not None and len(self.ids):
+            if self.data.cols != vector.shape[0]:
+                raise nat.MarlinArgumentError(nat.MB_ERR_DIM_MISMATCH, "Dimension mismatch during matrix-vector multiplication: "
+                                              f"{self.data.cols} vs {vector.shape[0]}")
+            y = self.data.multiply(SubMatrix(vector.reshape(-1, 1), device=self.data.buf.device))
+            parts = [(self.ids, y.toBreeze().reshape(-1))]
+        parts = self._gather(parts)
+        total = int(sum(len(i) for i, _ in parts))
+        out = np.zeros(total)
+        for ids, vals in parts:
+            out[ids] = vals                                               # result(id) = v   (:181-183)
+        return out
 
     def _multiply_local(self, B) -> "DenseVecMatrix":
         """multiply(B: BDM[Double]) :1660-1680 — B replicated on every rank (sc.broadcast), one GEMM per row shard,

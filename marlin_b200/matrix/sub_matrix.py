@@ -203,6 +203,22 @@ class SubMatrix:
         nat.check(rt.lib.mb_block_gemm(rt.ctx, self.handle(), other.handle(), out.handle(), int(accumulate)))
         return out
 
+    def dot(self, other: "SubMatrix") -> float:
+        """Breeze `v.t * w` of two single-column (or single-row) blocks (matrix/DistributedVector.scala:167)."""
+        rt = Runtime.get(); rt.sync_stream()
+        out = C.c_double()
+        nat.check(rt.lib.mb_block_dot(rt.ctx, self.handle(), other.handle(), C.byref(out)))
+        return float(out.value)
+
+    def outer(self, other: "SubMatrix") -> "SubMatrix":
+        """Breeze `v * w.t` (matrix/DistributedVector.scala:157): rank-1 block of two vectors."""
+        rt = Runtime.get(); rt.sync_stream()
+        n0 = self._rows * self._cols
+        n1 = other._rows * other._cols
+        out = SubMatrix.empty(n0, n1, nat.MB_F64, self.buf.device)
+        nat.check(rt.lib.mb_block_ger(rt.ctx, self.handle(), other.handle(), out.handle()))
+        return out
+
     def add_(self, other: "SubMatrix") -> "SubMatrix":
         """In-place accumulate (the reduceByKey combine of BlockMatrix.scala:177 without a new allocation)."""
         rt = Runtime.get(); rt.sync_stream()

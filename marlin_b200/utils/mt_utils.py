@@ -137,6 +137,44 @@ class MTUtils:
             blocks.append((BlockID(i, j), blk))
         return BlockMatrix(blocks, nRows, nColumns, by_row, by_col)
 
+    @staticmethod
+    def randomDistVector(sc, length: int, numSplits: int, distribution: Optional[UniformGenerator] = None,
+                         seed: Optional[int] = None):
+        """utils/MTUtils.scala:86-93 -> RandomDistVectorRDD (rdd/RandomRDD.scala:116-134,103-112): one partition per
+        piece, piece i = the first splitLength values of the stream seeded with the i-th nextLong of Random(seed);
+        the last piece takes the remainder."""
+        from ..matrix.distributed_vector import DistributedVector
+        dist_ = distribution or UniformGenerator(0.0, 1.0)
+        if seed is None:
+            seed = time.time_ns()
+        seeds = MTUtils._partition_seeds(seed, numSplits)
+        rank, ws = world()
+        split_len = int(math.ceil(float(length) / float(numSplits)))
+        pieces = []
+        for i in range(numSplits):
+            if ws > 1 and i % ws != rank:
+                continue
+            n = length - split_len * i if i == numSplits - 1 else split_len
+            blk = SubMatrix.empty(n, 1, nat.MB_F64)
+            MTUtils._fill(blk, seeds[i], 0, dist_, row_major=False)
+            pieces.append((i, blk))
+        return DistributedVector(pieces, length, numSplits)
+
+    @staticmethod
+    def onesDistVector(sc, length: int, numSplits: int):
+        """utils/MTUtils.scala:128-134 (OnesGenerator pieces)."""
+        from ..matrix.distributed_vector import DistributedVector
+        rank, ws = world()
+        split_len = int(math.ceil(float(length) / float(numSplits)))
+        pieces = []
+        for i in range(numSplits):
+            if ws > 1 and i % ws != rank:
+                continue
+            n = length - split_len * i if i == numSplits - 1 else split_len
+            blk = SubMatrix.zeros(n, 1, nat.MB_F64)
+            pieces.append((i, blk.add(1.0)))
+        return DistributedVector(pieces)
+
     # ------------------------------------------------------------------ split chooser
     @staticmethod
     def splitMethod(m: int, k: int, n: int, cores: int) -> Tuple[int, int, int]:

@@ -14,6 +14,8 @@
  *     unless native BLAS is installed).  mo_dgemm_f2j below follows dgemm.f's loop nests and —
  *     because the JVM never contracts a*b+c into an FMA — is compiled with -ffp-contract=off so every
  *     multiply and add rounds separately, exactly as F2J does.
+ *   - SubMatrix.multiply(v: Vector) (matrix/SubMatrix.scala:131-139) = Breeze `BDM * BDV` = netlib dgemv, and
+ *     DistributedVector.multiply's `v.t * w` = ddot (matrix/DistributedVector.scala:167): mo_dgemv_f2j, mo_ddot_f2j.
  *   - SubMatrix.add / subtract / scalar ops (matrix/SubMatrix.scala:41-85,123-131) = Breeze
  *     element-wise operators; BlockMatrix.transpose's `denseBlock.t.copy` (matrix/BlockMatrix.scala:517).
  *   - MTUtils.hashSeed (utils/MTUtils.scala:18-21), XORShiftRandom.next
@@ -102,6 +104,54 @@ int mo_dgemm_f2j(char transa, char transb, int m, int n, int k, double alpha, co
 #undef B
 #undef Cc
     return 0;
+}
+
+/* reference-BLAS dgemv.f (netlib-java F2J), unit strides: y := alpha*op(A)*x + beta*y.  Breeze `BDM * BDV`
+ * (SubMatrix.multiply(v: Vector), matrix/SubMatrix.scala:131-139) calls it with alpha = 1, beta = 0. */
+int mo_dgemv_f2j(char trans, int m, int n, double alpha, const double* a, long a_off, int lda, const double* x,
+                 double beta, double* y) {
+    const int nota = (trans == 'N' || trans == 'n');
+    if (!nota && !(trans == 'T' || trans == 't' || trans == 'C' || trans == 'c')) return 1;
+    if (m < 0) return 2;
+    if (n < 0) return 3;
+    if (lda < (m > 1 ? m : 1)) return 6;
+    if (m == 0 || n == 0 || (alpha == 0.0 && beta == 1.0)) return 0;
+    a += a_off;
+    const int leny = nota ? m : n;
+    if (beta != 1.0) {
+        if (beta == 0.0) for (int i = 0; i < leny; ++i) y[i] = 0.0;
+        else for (int i = 0; i < leny; ++i) y[i] = beta * y[i];
+    }
+    if (alpha == 0.0) return 0;
+    if (nota) {
+        for (int j = 0; j < n; ++j) {
+            if (x[j] != 0.0) {
+                const double temp = alpha * x[j];
+                for (int i = 0; i < m; ++i) y[i] = y[i] + temp * a[(long)i + (long)j * lda];
+            }
+        }
+    } else {
+        for (int j = 0; j < n; ++j) {
+            double temp = 0.0;
+            for (int i = 0; i < m; ++i) temp = temp + a[(long)i + (long)j * lda] * x[i];
+            y[j] = y[j] + alpha * temp;
+        }
+    }
+    return 0;
+}
+
+/* reference-BLAS ddot.f (unit strides: clean-up loop of n mod 5, then five products per statement, summed left to
+ * right).  Breeze `v.t * w` (matrix/DistributedVector.scala:167). */
+double mo_ddot_f2j(long n, const double* dx, const double* dy) {
+    double dtemp = 0.0;
+    if (n <= 0) return dtemp;
+    const long m = n % 5;
+    for (long i = 0; i < m; ++i) dtemp = dtemp + dx[i] * dy[i];
+    if (n < 5) return dtemp;
+    for (long i = m; i < n; i += 5)
+        dtemp = dtemp + dx[i] * dy[i] + dx[i + 1] * dy[i + 1] + dx[i + 2] * dy[i + 2] + dx[i + 3] * dy[i + 3] +
+                dx[i + 4] * dy[i + 4];
+    return dtemp;
 }
 
 /* Breeze element-wise binary operators on packed arrays (SubMatrix.add/subtract, dotProduct). op: 0 +, 1 -, 2 * */

@@ -51,6 +51,10 @@ def clib() -> C.CDLL:
         lib.mo_dgemm_f2j.restype = C.c_int
         lib.mo_dgemm_f2j.argtypes = [C.c_char, C.c_char, C.c_int, C.c_int, C.c_int, C.c_double, dp, C.c_long, C.c_int,
                                      dp, C.c_long, C.c_int, C.c_double, dp, C.c_long, C.c_int]
+        lib.mo_dgemv_f2j.restype = C.c_int
+        lib.mo_dgemv_f2j.argtypes = [C.c_char, C.c_int, C.c_int, C.c_double, dp, C.c_long, C.c_int, dp, C.c_double, dp]
+        lib.mo_ddot_f2j.restype = C.c_double
+        lib.mo_ddot_f2j.argtypes = [C.c_long, dp, dp]
         lib.mo_binary.argtypes = [C.c_int, C.c_long, dp, dp, dp]
         lib.mo_transpose_copy.argtypes = [C.c_int, C.c_int, dp, C.c_long, dp]
         lib.mo_hash_seed.restype = C.c_int64
@@ -109,6 +113,45 @@ def block_multiply(a: np.ndarray, b: np.ndarray, gemm: str = "f2j") -> np.ndarra
     dgemm_f2j(ta, tb, m, n, k, 1.0, abuf.reshape(-1, order="A"), 0, lda, bbuf.reshape(-1, order="A"), 0, ldb, 0.0,
               c.reshape(-1, order="F"), 0, max(1, m))
     return c
+
+
+def block_multiply_vector(a: np.ndarray, x: np.ndarray) -> np.ndarray:
+    """SubMatrix.multiply(v: Vector) (matrix/SubMatrix.scala:131-139): `denseBlock * v.inner.get` -> Breeze ->
+    dgemv(transString(a), storedRows, storedCols, 1.0, a.data, a.offset, a.majorStride, x, 0.0, y).  A C-contiguous
+    array plays the isTranspose view, as in block_multiply."""
+    x = np.ascontiguousarray(x, dtype=np.float64).reshape(-1)
+    if a.shape[1] != x.shape[0]:
+        raise ValueError(f"Dimension mismatch: {a.shape[1]} vs {x.shape[0]}")
+    y = np.zeros(a.shape[0])
+    if a.size == 0:
+        return y
+    if a.flags.f_contiguous:
+        info = clib().mo_dgemv_f2j(b"N", a.shape[0], a.shape[1], 1.0, _dp(a), 0, max(1, a.shape[0]), _dp(x), 0.0, _dp(y))
+    elif a.flags.c_contiguous:
+        info = clib().mo_dgemv_f2j(b"T", a.shape[1], a.shape[0], 1.0, _dp(a), 0, max(1, a.shape[1]), _dp(x), 0.0, _dp(y))
+    else:
+        af = _f(a)
+        info = clib().mo_dgemv_f2j(b"N", af.shape[0], af.shape[1], 1.0, _dp(af), 0, max(1, af.shape[0]), _dp(x), 0.0, _dp(y))
+    if info:
+        raise ValueError(f"dgemv: illegal argument {info}")
+    return y
+
+
+def vector_dot(x: np.ndarray, y: np.ndarray) -> float:
+    """Breeze `v.t * w` -> ddot (matrix/DistributedVector.scala:167)."""
+    x = np.ascontiguousarray(x, dtype=np.float64).reshape(-1)
+    y = np.ascontiguousarray(y, dtype=np.float64).reshape(-1)
+    if x.shape != y.shape:
+        raise ValueError("the length of these two vectors are not the same")
+    return float(clib().mo_ddot_f2j(x.shape[0], _dp(x), _dp(y)))
+
+
+def vector_outer(x: np.ndarray, y: np.ndarray) -> np.ndarray:
+    """Breeze `v * w.t` (matrix/DistributedVector.scala:157): the column vector as an n x 1 matrix times the 1 x n row,
+    i.e. dgemm with k = 1."""
+    x = np.asarray(x, dtype=np.float64).reshape(-1, 1)
+    y = np.asarray(y, dtype=np.float64).reshape(1, -1)
+    return block_multiply(_f(x), _f(y))
 
 
 def block_add(a: np.ndarray, b: np.ndarray) -> np.ndarray:
@@ -312,6 +355,31 @@ class BlockMatrix:
             acc[(r, 0)] = block_add(acc[(r, 0)], p) if (r, 0) in acc else p
         # the reference reports numBlksByCol() here although all keys have column 0 (:301)
         return BlockMatrix(list(acc.items()), self.num_rows(), B.shape[1], self.num_blks_by_row(), self.num_blks_by_col())
+
+    def multiply_dist_vector(self, v: "DistributedVector") -> "DistributedVector":
+        """multiply(v: DistributedVector) :240-259 — every vector piece goes to the blocks of its block column, block x
+        piece, reduceByKey(add) over the block row (ascending column here).  The result is labelled with v's length
+        and split count (:252,257), as the reference does."""
+        if self.num_cols() != v.length():
+            raise ValueError(f"Dimension mismatch during matrix-matrix multiplication {self.num_cols()} v.s {v.length()}")
+        if self.num_blks_by_col() != v.split_num():
+            raise ValueError("not supported matrix or vector")
+        pieces = dict(v.vectors)
+        acc: Dict[int, np.ndarray] = {}
+        for (r, c), blk in sorted(self.blocks, key=lambda t: t[0]):
+            p = block_multiply_vector(blk, pieces[c])
+            acc[r] = acc[r] + p if r in acc else p
+        return DistributedVector(sorted(acc.items()), v.length(), v.split_num())
+
+    def multiply_vector(self, v: np.ndarray) -> "DistributedVector":
+        """multiply(v: BDV[Double]) :265-274 — broadcast vector, one block column only."""
+        v = np.asarray(v, dtype=np.float64).reshape(-1)
+        if self.num_cols() != v.shape[0]:
+            raise ValueError(f"matrix columns size {self.num_cols()} not support vector length {v.shape[0]}")
+        if self.num_blks_by_col() != 1:
+            raise ValueError("should not split the matrix by column")
+        res = [(r, block_multiply_vector(blk, v)) for (r, c), blk in sorted(self.blocks, key=lambda t: t[0])]
+        return DistributedVector(res, self.num_rows(), self.num_blks_by_row())
 
     def multiply_auto(self, other, cores: int, broadcast_threshold: int = 300, gemm: str = "f2j"):
         """multiply(other, cores, broadcastThreshold) :87-122"""
@@ -519,6 +587,24 @@ class DenseVecMatrix:
             res.append((key, acc))
         return BlockMatrix(res, self.num_rows(), other.num_cols(), m, n)
 
+    def multiply_dist_vector(self, v: "DistributedVector", split_mode: Tuple[int, int]) -> "DistributedVector":
+        """multiply(vector: DistributedVector, splitMode) matrix/DenseVecMatrix.scala:149-154"""
+        if self.num_cols() != v.length():
+            raise ValueError(f"Dimension mismatch during matrix-matrix multiplication: {self.num_cols()} vs {v.length()}")
+        m, k = split_mode
+        return self.to_block_matrix(m, k).multiply_dist_vector(v)
+
+    def multiply_vector(self, v: np.ndarray, split_mode: Optional[int] = None):
+        """multiply(vector: BDV, splitMode) :162-165 -> DistributedVector; multiply(vector: BDV) :171-184 -> the local
+        vector of row . vector products (`v.t * vec` = ddot per row)."""
+        v = np.asarray(v, dtype=np.float64).reshape(-1)
+        if split_mode is not None:
+            return self.to_block_matrix(split_mode, 1).multiply_vector(v)
+        out = np.zeros(len(self.rows))
+        for i, row in self.rows:
+            out[int(i)] = vector_dot(row, v)
+        return out
+
     def multiply_local(self, B: np.ndarray, gemm: str = "f2j", partitions: int = 2) -> "DenseVecMatrix":
         """multiply(B: BDM) :1660-1680 — per partition: rowsMat(::, i) := row_i (K x rowsInPart),
         matrix = B^T.copy * rowsMat, emit column i as row i."""
@@ -594,6 +680,93 @@ class DenseVecMatrix:
     def save_lines(self) -> List[str]:
         """saveToFileSystem :1042-1046: `index:v,v,...`"""
         return [f"{i}:" + ",".join(_jdouble(x) for x in v) for i, v in self.rows]
+
+
+class DistributedVector:
+    """matrix/DistributedVector.scala:16-186.  vectors: list of (id, 1-D ndarray)."""
+
+    def __init__(self, vectors, length: int = 0, splits: int = 0):
+        self.vectors = [(int(i), np.array(v, dtype=np.float64).reshape(-1)) for i, v in vectors]
+        self._len, self._splits = int(length), int(splits)
+        self.column_major = True
+
+    def split_num(self) -> int:                     # :31-36
+        if self._splits <= 0:
+            self._splits = len(self.vectors)
+        return self._splits
+
+    def length(self) -> int:                        # :38-43
+        if self._len <= 0:
+            self._len = sum(v.shape[0] for _, v in self.vectors)
+        return self._len
+
+    def substract(self, other: "DistributedVector") -> "DistributedVector":          # :45-49 (sic)
+        if self.length() != other.length():
+            raise ValueError(f"unsupported vector length: {self.length()} v.s {other.length()}")
+        theirs = dict(other.vectors)
+        return DistributedVector([(i, v - theirs[i]) for i, v in self.vectors if i in theirs], other.length(), self.split_num())
+
+    def transpose(self) -> "DistributedVector":      # :56-60
+        out = DistributedVector(self.vectors, self.length(), self.split_num())
+        out.column_major = False
+        return out
+
+    def to_breeze(self) -> np.ndarray:               # :65-73 — piece id starts at id * (length / pieces), integer division
+        out = np.zeros(self.length())
+        offset = self.length() // len(self.vectors)
+        for i, v in self.vectors:
+            if i * offset + v.shape[0] > out.shape[0]:
+                raise IndexError("slice out of bounds")
+            out[i * offset:i * offset + v.shape[0]] = v
+        return out
+
+    def to_dis_vector(self, split_status_by_row, split_num: int) -> "DistributedVector":     # :84-107
+        most = _ceil_div_d(self.length(), split_num)
+        groups: Dict[int, list] = {}
+        for pid, (_, vec) in enumerate(self.vectors):         # one vector per partition (iter.next())
+            for vec_id, (old_start, old_end), (new_start, new_end) in split_status_by_row[pid]:
+                groups.setdefault(vec_id, []).append((new_start, new_end, vec[old_start:old_end + 1]))
+        out = []
+        for vec_id, parts in sorted(groups.items()):
+            vlen = self.length() - vec_id * most if (vec_id + 1) * most > self.length() else most
+            v = np.zeros(vlen)
+            for s0, s1, piece in parts:
+                v[s0:s1 + 1] = piece
+            out.append((vec_id, v))
+        return DistributedVector(out)
+
+    def multiply(self, other: "DistributedVector", mode: str = "dist"):                      # :146-180
+        """column x row -> BlockMatrix of outer products; row x column -> Double."""
+        if self.length() != other.length():
+            raise ValueError("the length of these two vectors are not the same")
+        if self.split_num() != other.split_num():
+            raise ValueError("currently, only support two vectors with the same splits")
+        if self.column_major and not other.column_major:
+            theirs = dict(other.vectors)
+            blocks = [((i, j), vector_outer(v, theirs[j])) for i, v in self.vectors for j in range(self.split_num()) if j in theirs]
+            return BlockMatrix(blocks, self.length(), self.length(), self.split_num(), self.split_num())
+        if not self.column_major and other.column_major:
+            if mode.lower() == "dist":
+                theirs = dict(other.vectors)
+                total = None
+                for i, v in sorted(self.vectors):
+                    if i in theirs:
+                        d = vector_dot(v, theirs[i])
+                        total = d if total is None else total + d
+                if total is None:
+                    raise RuntimeError("empty collection")
+                return total
+            if mode.lower() == "local":
+                return vector_dot(self.to_breeze(), other.to_breeze())
+            raise ValueError("unrecognized mode")
+        raise ValueError("the columnMajor status of the two distributed vectors are the same")
+
+    @staticmethod
+    def from_vector(vector: np.ndarray, num_splits: int) -> "DistributedVector":             # :184-190
+        vector = np.asarray(vector, dtype=np.float64).reshape(-1)
+        vlen = _ceil_div_d(vector.shape[0], num_splits)
+        pieces = [(i, vector[i * vlen:min((i + 1) * vlen, vector.shape[0])]) for i in range(num_splits)]
+        return DistributedVector(pieces, vector.shape[0], num_splits)
 
 
 def _partition(seq: list, parts: int) -> List[list]:

@@ -57,7 +57,24 @@ for n in (8192, 16384):
         ms = timeit(fn)
         gbs = elems * bpe / ms / 1e6
         res[name] = {"ms": ms, "GB/s": gbs, "frac_of_measured_hbm": gbs / HBM}
+    # vector side: the matrix crosses HBM once; vectors are noise
+    xv, yv = mb.SubMatrix.empty(n, 1), mb.SubMatrix.empty(n, 1)
+    nat.check(lib.mb_fill_uniform(ctx, xv.handle(), 3, 0, 0.0, 1.0, 0))
+    At = A.t
+    vec_cases = {
+        "gemv y=A x (8 B/elem)": (lambda: nat.check(lib.mb_block_gemv(ctx, A.handle(), xv.handle(), yv.handle(), 0)), 8),
+        "gemv y=A^T-view x, row-major rows (8 B/elem)": (lambda: nat.check(lib.mb_block_gemv(ctx, At.handle(), xv.handle(), yv.handle(), 0)), 8),
+        "ger out=x y^T (8 B/elem written)": (lambda: nat.check(lib.mb_block_ger(ctx, xv.handle(), yv.handle(), O.handle())), 8),
+    }
+    for name, (fn, bpe) in vec_cases.items():
+        ms = timeit(fn)
+        gbs = elems * bpe / ms / 1e6
+        res[name] = {"ms": ms, "GB/s": gbs, "frac_of_measured_hbm": gbs / HBM}
     s = C.c_double()
+    Aflat = mb.SubMatrix(buf=A.buf, rows=elems, cols=1, ld=elems)
+    Bflat = mb.SubMatrix(buf=B.buf, rows=elems, cols=1, ld=elems)
+    ms = timeit(lambda: nat.check(lib.mb_block_dot(ctx, Aflat.handle(), Bflat.handle(), C.byref(s))))
+    res["dot (2*8 B/elem, incl. D2H of the scalar)"] = {"ms": ms, "GB/s": elems * 16 / ms / 1e6, "frac_of_measured_hbm": elems * 16 / ms / 1e6 / HBM}
     ms = timeit(lambda: nat.check(lib.mb_block_sum(ctx, A.handle(), C.byref(s))))
     res["sum (8 B/elem, incl. D2H of the scalar)"] = {"ms": ms, "GB/s": elems * 8 / ms / 1e6, "frac_of_measured_hbm": elems * 8 / ms / 1e6 / HBM}
     ta = torch.empty(elems, dtype=torch.float64, device="cuda")
@@ -65,11 +82,11 @@ for n in (8192, 16384):
     ms = timeit(lambda: tb.copy_(ta))
     res["torch copy_ yardstick (2*8 B/elem)"] = {"ms": ms, "GB/s": elems * 16 / ms / 1e6}
     hbm[f"{n}x{n} fp64"] = res
-    del A, B, O, T, ta, tb
+    del A, B, O, T, ta, tb, At, Aflat, Bflat
 out["hbm_kernels"] = hbm
 
 gemm = {}
-for n in (4096, 8192, 16384):
+for n in (() if "hbm" in sys.argv[1:] else (4096, 8192, 16384)):
     A = mb.MTUtils.randomBlockMatrix(None, n, n, 1, 1, seed=3, dtype=nat.MB_BF16).blocks[0][1]
     B = mb.MTUtils.randomBlockMatrix(None, n, n, 1, 1, seed=4, dtype=nat.MB_BF16).blocks[0][1]
     Cm = mb.SubMatrix.empty(n, n, nat.MB_F32)

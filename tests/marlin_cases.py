@@ -40,3 +40,16 @@ CFG1 = {"sumA": -8.317421000000003, "sumB": 47.658801000000025, "sumAplusB": 39.
         "sumC": 449.0644284029081, "traceC": -54.83429525636101, "frobC": 333.20829594580283}
 SHA256 = {"a.100.100": "4cf2e6c125eb237810d5729c8154ed5ff97b08737363c581302bfa1bb7c76eb9",
           "b.100.100": "447f2e645563e0e08ca61bc748b0633da9f4865b8a11f83e4b0758ce8cb0e6b1"}
+
+# DistributedMatrixSuite.scala:121-143 "disVec to disVec": three pieces re-split into four
+DISVEC_PIECES = [(0, [0.0, 1.0, 2.0, 3.0]), (1, [4.0, 5.0, 6.0, 7.0]), (2, [8.0, 9.0, 10.0, 11.0])]
+DISVEC_SPLIT_STATUS = [[(0, (0, 2), (0, 2)), (1, (3, 3), (0, 0))],
+                       [(1, (0, 1), (1, 2)), (2, (2, 3), (0, 1))],
+                       [(2, (0, 0), (2, 2)), (3, (1, 3), (0, 2))]]
+# :390-409 "BLAS1 distributed vector multiplication"
+BLAS1_PIECES = [(0, [1.0, 2.0]), (1, [3.0, 4.0])]
+BLAS1_OUTER = np.array([[1.0, 2.0, 3.0, 4.0], [2.0, 4.0, 6.0, 8.0], [3.0, 6.0, 9.0, 12.0], [4.0, 8.0, 12.0, 16.0]])
+BLAS1_INNER = 30.0
+# not in the reference suite (it has no matrix x vector test): A . [1,2,3,4] for the 4x4 matrix above, exact
+MATVEC_X = [1.0, 2.0, 3.0, 4.0]
+MATVEC_Y = EXPECTED_DENSE @ np.array(MATVEC_X)

@@ -194,3 +194,43 @@ def test_save_load_roundtrip(oracle):
     again = oracle.load_block_matrix_lines(blk.save_block_lines())
     assert np.array_equal(again.to_breeze(), mc.EXPECTED_DENSE)
     assert blk.save_block_lines()[0] == "0-0-2-2:0.0,2.0,1.0,3.0"
+
+
+def test_disvec_to_disvec(oracle):                        # DMS.scala:121-143
+    v1 = oracle.DistributedVector([(i, np.array(v)) for i, v in mc.DISVEC_PIECES])
+    v2 = v1.to_dis_vector(mc.DISVEC_SPLIT_STATUS, 4)
+    assert [i for i, _ in v2.vectors] == [0, 1, 2, 3] and all(v.shape[0] == 3 for _, v in v2.vectors)
+    assert np.array_equal(v1.to_breeze(), v2.to_breeze())
+    assert np.array_equal(v1.to_breeze(), np.arange(12.0))
+
+
+def test_blas1_distributed_vector(oracle):                # DMS.scala:390-409
+    pieces = [(i, np.array(v)) for i, v in mc.BLAS1_PIECES]
+    v1, v2 = oracle.DistributedVector(pieces), oracle.DistributedVector(pieces)
+    assert np.array_equal(v1.multiply(v2.transpose()).to_breeze(), mc.BLAS1_OUTER)
+    assert v1.transpose().multiply(v2) == mc.BLAS1_INNER
+    assert v1.transpose().multiply(v2, "local") == mc.BLAS1_INNER
+    with pytest.raises(ValueError):
+        v1.multiply(v2)                                   # same orientation (DistributedVector.scala:177-179)
+    with pytest.raises(ValueError):
+        v1.transpose().multiply(v2, "elsewhere")
+
+
+def test_matrix_vector(oracle):                           # BlockMatrix.scala:240-274, DenseVecMatrix.scala:149-184
+    x = np.array(mc.MATVEC_X)
+    ma, mat = _blk(oracle), _dvm(oracle)
+    dv = oracle.DistributedVector.from_vector(x, 2)
+    assert np.array_equal(ma.multiply_dist_vector(dv).to_breeze(), mc.MATVEC_Y)
+    assert np.array_equal(mat.multiply_dist_vector(dv, (2, 2)).to_breeze(), mc.MATVEC_Y)
+    assert np.array_equal(mat.multiply_vector(x, 2).to_breeze(), mc.MATVEC_Y)
+    assert np.array_equal(mat.multiply_vector(x), mc.MATVEC_Y)
+    with pytest.raises(ValueError):
+        ma.multiply_vector(x)                             # "should not split the matrix by column" (:267)
+    with pytest.raises(ValueError):
+        ma.multiply_dist_vector(oracle.DistributedVector.from_vector(x, 4))
+    rng = np.random.default_rng(5)
+    A, xx = np.asfortranarray(rng.standard_normal((37, 23))), rng.standard_normal(23)
+    for arr in (A, np.ascontiguousarray(A)):              # plain and isTranspose operands of dgemv
+        y = oracle.block_multiply_vector(arr, xx)
+        assert np.abs(y - A @ xx).max() <= 1e-13
+    assert abs(oracle.vector_dot(xx, xx) - float(xx @ xx)) <= 1e-13
