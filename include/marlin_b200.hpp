@@ -11,6 +11,7 @@
 #include "marlin_b200.h"
 
 #include <algorithm>
+#include <cctype>
 #include <cmath>
 #include <cstdint>
 #include <fstream>
@@ -140,6 +141,18 @@ public:
         check(mb_block_transpose(Context::get(), h_.get(), r.h_.get()));
         return r;
     }
+    // vectors are single-column blocks: BDM * BDV goes through multiply() above (dgemv), v.t * w and v * w.t here
+    explicit SubMatrix(const std::vector<double>& v) {                                // new DenseVector(array)
+        mb_block* b = nullptr;
+        check(mb_block_upload(Context::get(), v.data(), 0, (int)v.size(), 1, std::max<int>(1, (int)v.size()), 0, MB_F64, &b));
+        own(b);
+    }
+    double dot(const SubMatrix& o) const { double d = 0; check(mb_block_dot(Context::get(), h_.get(), o.h_.get(), &d)); return d; }      // DistributedVector.scala:167
+    SubMatrix outer(const SubMatrix& o) const {                                       // DistributedVector.scala:157
+        SubMatrix r = empty(rows() * cols(), o.rows() * o.cols());
+        check(mb_block_ger(Context::get(), h_.get(), o.h_.get(), r.h_.get()));
+        return r;
+    }
     void assign(const SubMatrix& src) { check(mb_block_copy(Context::get(), src.h_.get(), h_.get())); }   // this(range) := src
     double sum() const { double s = 0; check(mb_block_sum(Context::get(), h_.get(), &s)); return s; }
     DenseMatrix denseBlock() const {                                                  // collect to the host (toBreeze)
@@ -159,6 +172,7 @@ private:
 };
 
 class DenseVecMatrix;
+class DistributedVector;
 
 // ---------------------------------------------------------------------------------------------- BlockMatrix
 class BlockMatrix {
@@ -274,6 +288,8 @@ public:
         return multiply(other, std::make_tuple(mkn[0], mkn[1], mkn[2]));
     }
     inline BlockMatrix multiply(DenseVecMatrix& other, int cores, int broadcastThreshold = 300);     // :93-109
+    inline DistributedVector multiply(DistributedVector& v);                                         // :240-259
+    inline DistributedVector multiply(const std::vector<double>& v);                                 // multiply(v: BDV) :265-274
     BlockMatrix multiply(double b) { return mapBlocks([&](const SubMatrix& s) { return s.multiply(b); }); }     // :229-232
     // multiply(B: BDM[Double]) :280-303
     BlockMatrix multiply(const DenseMatrix& Bm) {
@@ -588,6 +604,159 @@ inline BlockMatrix BlockMatrix::multiply(DenseVecMatrix& other, int cores, int b
     }
     BlockMatrix a = toBlockMatrix(mkn[0], mkn[1]), b = other.toBlockMatrix(mkn[1], mkn[2]);
     return a.multiply(b);
+}
+
+// ---------------------------------------------------------------------------------------------- DistributedVector
+// matrix/DistributedVector.scala — RDD[(Int, DenseVector)] becomes (id, n x 1 block) pairs in HBM.
+class DistributedVector {
+public:
+    using Pieces = std::vector<std::pair<int, SubMatrix>>;
+    // (vecId, (oldStart, oldEnd), (newStart, newEnd)) per source partition (:84)
+    using SplitStatus = std::vector<std::vector<std::tuple<int, std::pair<int, int>, std::pair<int, int>>>>;
+    Pieces vectors;
+
+    explicit DistributedVector(Pieces v, long len = 0, int splits = 0) : vectors(std::move(v)), len_(len), splits_(splits) {}
+    explicit DistributedVector(const std::vector<std::pair<int, std::vector<double>>>& host, long len = 0, int splits = 0)
+        : len_(len), splits_(splits) {
+        for (auto& kv : host) vectors.emplace_back(kv.first, SubMatrix(kv.second));
+    }
+    bool isColumnMajor() const { return columnMajor_; }
+    void setColumnMajor(bool b) { columnMajor_ = b; }
+    int splitNum() { if (splits_ <= 0) splits_ = (int)vectors.size(); return splits_; }                 // :31-36
+    long length() {                                                                                     // :38-43
+        if (len_ <= 0) { long s = 0; for (auto& kv : vectors) s += kv.second.rows(); len_ = s; }
+        return len_;
+    }
+    const Pieces& getVectors() const { return vectors; }
+
+    DistributedVector substract(DistributedVector& v) {                                                 // :45-49 (sic)
+        if (length() != v.length())
+            throw std::invalid_argument("unsupported vector length: " + std::to_string(length()) + " v.s " + std::to_string(v.length()));
+        Pieces res;
+        for (auto& a : vectors)
+            for (auto& b : v.vectors)
+                if (a.first == b.first) res.emplace_back(a.first, a.second.subtract(b.second));
+        return DistributedVector(res, v.length(), splitNum());
+    }
+    DistributedVector transpose() {                                                                     // :56-60
+        DistributedVector r(vectors, length(), splitNum());
+        r.setColumnMajor(false);
+        return r;
+    }
+    std::vector<double> toBreeze() {                                                                    // :65-73
+        std::vector<double> out((size_t)length(), 0.0);
+        const long offset = length() / (long)vectors.size();
+        for (auto& kv : vectors) {
+            DenseMatrix d = kv.second.denseBlock();
+            if (kv.first * offset + (long)d.data.size() > (long)out.size()) throw std::out_of_range("slice out of bounds");
+            std::copy(d.data.begin(), d.data.end(), out.begin() + kv.first * offset);
+        }
+        return out;
+    }
+    DistributedVector toDisVector(const SplitStatus& splitStatusByRow, int splitNum) {                  // :84-107
+        const long n = length();
+        const int most = ceilLen(n, splitNum);
+        Pieces sorted = vectors;
+        std::sort(sorted.begin(), sorted.end(), [](auto& a, auto& b) { return a.first < b.first; });
+        std::map<int, SubMatrix> out;
+        for (size_t pid = 0; pid < splitStatusByRow.size(); ++pid)
+            for (auto& st : splitStatusByRow[pid]) {
+                const int vecId = std::get<0>(st);
+                auto it = out.find(vecId);
+                if (it == out.end()) {
+                    const int vlen = (long)(vecId + 1) * most > n ? (int)(n - (long)vecId * most) : most;
+                    SubMatrix z = SubMatrix::empty(vlen, 1);
+                    check(mb_block_fill(Context::get(), z.handle(), 0.0));
+                    it = out.emplace(vecId, z).first;
+                }
+                const auto oldR = std::get<1>(st), newR = std::get<2>(st);
+                SubMatrix dst = it->second.slice(newR.first, newR.second + 1, 0, 1);
+                dst.assign(sorted[pid].second.slice(oldR.first, oldR.second + 1, 0, 1));
+            }
+        Pieces res(out.begin(), out.end());
+        return DistributedVector(res);
+    }
+    // Either[Double, BlockMatrix] (:146-180)
+    struct Product {
+        bool isLeft = false;
+        double left = 0.0;
+        std::shared_ptr<BlockMatrix> right;
+    };
+    Product multiply(DistributedVector& other, const std::string& mode = "dist") {
+        if (length() != other.length()) throw std::invalid_argument("the length of these two vectors are not the same");
+        if (splitNum() != other.splitNum()) throw std::invalid_argument("currently, only support two vectors with the same splits");
+        Product p;
+        if (columnMajor_ && !other.columnMajor_) {
+            BlockMatrix::Blocks blocks;
+            for (auto& a : vectors)
+                for (auto& b : other.vectors) blocks.emplace_back(BlockID(a.first, b.first), a.second.outer(b.second));
+            p.right = std::make_shared<BlockMatrix>(blocks, length(), length(), splitNum(), splitNum());
+            return p;
+        }
+        if (!columnMajor_ && other.columnMajor_) {
+            std::string m = mode;
+            std::transform(m.begin(), m.end(), m.begin(), [](unsigned char c) { return (char)std::tolower(c); });
+            p.isLeft = true;
+            if (m == "dist") {
+                Pieces sorted = vectors;
+                std::sort(sorted.begin(), sorted.end(), [](auto& a, auto& b) { return a.first < b.first; });
+                bool any = false;
+                for (auto& a : sorted)
+                    for (auto& b : other.vectors)
+                        if (a.first == b.first) { const double d = a.second.dot(b.second); p.left = any ? p.left + d : d; any = true; }
+                if (!any) throw std::runtime_error("empty collection");
+                return p;
+            }
+            if (m == "local") {
+                SubMatrix a(toBreeze()), b(other.toBreeze());
+                p.left = a.dot(b);
+                return p;
+            }
+            throw std::invalid_argument("unrecognized mode");
+        }
+        throw std::invalid_argument("the columnMajor status of the two distributed vectors are the same");
+    }
+    static DistributedVector fromVector(const std::vector<double>& vector, int numSplits) {             // :184-190
+        const int vecLen = ceilLen((long)vector.size(), numSplits);
+        Pieces pieces;
+        for (int i = 0; i < numSplits; ++i) {
+            const size_t a = std::min(vector.size(), (size_t)i * vecLen), b = std::min(vector.size(), (size_t)(i + 1) * vecLen);
+            pieces.emplace_back(i, SubMatrix(std::vector<double>(vector.begin() + a, vector.begin() + b)));
+        }
+        return DistributedVector(pieces, (long)vector.size(), numSplits);
+    }
+private:
+    long len_;
+    int splits_;
+    bool columnMajor_ = true;
+};
+
+inline DistributedVector BlockMatrix::multiply(DistributedVector& v) {
+    if (numCols() != v.length())
+        throw std::invalid_argument("Dimension mismatch during matrix-matrix multiplication " + std::to_string(numCols()) + " v.s " + std::to_string(v.length()));
+    if (numBlksByCol() != v.splitNum()) throw std::invalid_argument("not supported matrix or vector");
+    std::map<int, SubMatrix> pieces, acc;
+    for (auto& kv : v.vectors) pieces[kv.first] = kv.second;
+    Blocks sorted = blocks;
+    std::sort(sorted.begin(), sorted.end(), [](auto& a, auto& b) { return a.first < b.first; });
+    for (auto& kv : sorted) {
+        auto it = acc.find(kv.first.row);
+        if (it == acc.end()) acc[kv.first.row] = kv.second.multiply(pieces.at(kv.first.column));
+        else kv.second.multiplyInto(pieces.at(kv.first.column), it->second, true);     // reduceByKey(add) fused (:251)
+    }
+    DistributedVector::Pieces res(acc.begin(), acc.end());
+    return DistributedVector(res, v.length(), v.splitNum());                           // labelled as the reference does (:252)
+}
+inline DistributedVector BlockMatrix::multiply(const std::vector<double>& v) {
+    if (numCols() != (long)v.size())
+        throw std::invalid_argument("matrix columns size " + std::to_string(numCols()) + " not support vector length " + std::to_string(v.size()));
+    if (numBlksByCol() != 1) throw std::invalid_argument("should not split the matrix by column");
+    SubMatrix x(v);
+    DistributedVector::Pieces res;
+    Blocks sorted = blocks;
+    std::sort(sorted.begin(), sorted.end(), [](auto& a, auto& b) { return a.first < b.first; });
+    for (auto& kv : sorted) res.emplace_back(kv.first.row, kv.second.multiply(x));
+    return DistributedVector(res, numRows(), numBlksByRow());
 }
 
 // ---------------------------------------------------------------------------------------------- MTUtils

@@ -188,6 +188,40 @@ int main() {
         BlockMatrix blkMat(blks());
         CHECK(blkMat.multiply(expectedDense).toBreeze() == expectedProduct);
     });
+    test("disVec to disVec", [&] {                                                // :121-143
+        DistributedVector disVec1(std::vector<std::pair<int, std::vector<double>>>{
+            {0, {0.0, 1.0, 2.0, 3.0}}, {1, {4.0, 5.0, 6.0, 7.0}}, {2, {8.0, 9.0, 10.0, 11.0}}});
+        DistributedVector::SplitStatus splitStatus = {
+            {{0, {0, 2}, {0, 2}}, {1, {3, 3}, {0, 0}}},
+            {{1, {0, 1}, {1, 2}}, {2, {2, 3}, {0, 1}}},
+            {{2, {0, 0}, {2, 2}}, {3, {1, 3}, {0, 2}}}};
+        DistributedVector disVec2 = disVec1.toDisVector(splitStatus, 4);
+        CHECK(disVec2.splitNum() == 4);
+        CHECK(disVec1.toBreeze() == disVec2.toBreeze());
+    });
+    test("BLAS1 distributed vector multiplication", [&] {                         // :390-409
+        std::vector<std::pair<int, std::vector<double>>> vectors = {{0, {1.0, 2.0}}, {1, {3.0, 4.0}}};
+        DistributedVector disVec1(vectors), disVec2(vectors);
+        const BDM expected{{1.0, 2.0, 3.0, 4.0}, {2.0, 4.0, 6.0, 8.0}, {3.0, 6.0, 9.0, 12.0}, {4.0, 8.0, 12.0, 16.0}};
+        DistributedVector t2 = disVec2.transpose(), t1 = disVec1.transpose();
+        auto matResult = disVec1.multiply(t2);
+        auto doubleResult = t1.multiply(disVec2);
+        auto doubleResultLocal = t1.multiply(disVec2, "local");
+        CHECK(!matResult.isLeft && matResult.right->toBreeze() == expected);
+        CHECK(doubleResult.isLeft && doubleResult.left == 30.0);
+        CHECK(doubleResultLocal.isLeft && doubleResultLocal.left == 30.0);
+        CHECK(throws<std::invalid_argument>([&] { disVec1.multiply(disVec2); }));
+    });
+    test("matrix multiply a distributed / broadcast vector", [&] {                // BlockMatrix.scala:240-274
+        BlockMatrix ma(blks());
+        const std::vector<double> x = {1.0, 2.0, 3.0, 4.0}, y = {20.0, 40.0, 10.0, 10.0};
+        DistributedVector dv = DistributedVector::fromVector(x, 2);
+        CHECK(ma.multiply(dv).toBreeze() == y);
+        DenseVecMatrix mat(data());
+        BlockMatrix tall = mat.toBlockMatrix(2, 1);
+        CHECK(tall.multiply(x).toBreeze() == y);
+        CHECK(throws<std::invalid_argument>([&] { ma.multiply(x); }));
+    });
     // beyond the reference suite: error behaviour and the generators
     test("dimension mismatch is an IllegalArgumentException", [&] {               // BlockMatrix.scala:150-151, DenseVecMatrix.scala:199-200
         DenseVecMatrix a({{0, {1.0, 2.0, 3.0}}, {1, {4.0, 5.0, 6.0}}});

@@ -70,6 +70,19 @@ def main():
     assert (np.abs(ga.multiply(gb, (2, 2, 2)).toBreeze() - A @ B) / denom).max() <= 1e-10    # rows -> blocks across GPUs
     assert np.array_equal(ga.transpose().toBreeze(), A.T)
     assert np.array_equal(ga.add(ga).toBreeze(), 2 * A)
+    # ---- vector side: pieces on rank id mod G, block x piece on the block's GPU, row partials reduced across ranks
+    S = 600
+    Asq, xv = rng.random((S, S)), rng.random(S)
+    gsq = mb.DenseVecMatrix([(i, Asq[i]) for i in range(S) if i % ws == rank]).toBlockMatrix(3, 2)
+    dvec = mb.DistributedVector.fromVector(None, xv, 2)
+    dsq = np.abs(Asq) @ np.abs(xv)
+    assert (np.abs(gsq.multiply(dvec).toBreeze() - Asq @ xv) / dsq).max() <= 1e-10
+    gcol = mb.DenseVecMatrix([(i, Asq[i]) for i in range(S) if i % ws == rank])
+    assert (np.abs(gcol.multiply(xv, 3).toBreeze() - Asq @ xv) / dsq).max() <= 1e-10
+    assert (np.abs(gcol.multiply(xv) - Asq @ xv) / dsq).max() <= 1e-10
+    d1 = mb.DistributedVector.fromVector(None, xv, 4)
+    assert abs(d1.transpose().multiply(d1) - xv @ xv) <= 1e-10 * (xv @ xv)
+    assert np.array_equal(d1.multiply(d1.transpose()).toBreeze(), np.outer(xv, xv))
     # generators are partition-deterministic regardless of the number of GPUs
     g = mb.MTUtils.randomDenVecMatrix(None, 50, 7, numPartitions=4, seed=11)
     assert np.array_equal(g.toBreeze(), rm.random_den_vec_matrix(50, 7, 4, seed=11).to_breeze())

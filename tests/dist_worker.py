@@ -64,6 +64,17 @@ def main():
     dv = mb.DenseVecMatrix(rows, device=cpu)
     assert (dv.numRows(), dv.numCols()) == (8, 8)
     assert np.array_equal(dv.toBreeze(), A)
+    # DistributedVector: pieces live on rank id mod G; metadata gathers and the replication before a matrix x vector
+    v = np.arange(10.0)
+    dvec = mb.DistributedVector.fromVector(None, v, 3)                    # pieces 4, 4, 2
+    assert [i for i, _ in dvec.vectors] == [i for i in range(3) if i % 2 == rank]
+    assert dvec.length == 10 and dvec.splitNum == 3 and dvec.owner(2) == 0
+    lazy = mb.DistributedVector(dvec.vectors)                             # length / splitNum derived by a gather (:31-43)
+    assert lazy.length == 10 and lazy.splitNum == 3
+    rep = dvec._replicated()
+    assert sorted(rep) == [0, 1, 2] and [rep[i].rows for i in range(3)] == [4, 4, 2]
+    assert np.array_equal(np.concatenate([rep[i].toBreeze().reshape(-1) for i in range(3)]), v)
+    assert np.array_equal(mb.DistributedVector.fromVector(None, np.arange(12.0), 3).toBreeze(), np.arange(12.0))
     # compute entries still refuse to run on host memory
     try:
         am.blocks[0][1].multiply(bm.blocks[0][1])
