@@ -19,7 +19,7 @@ constexpr int GEMV_THREADS = 128;
 constexpr int GEMV_ROWS = GEMV_THREADS * 2;      // rows per CTA in the N kernel (one double2 per thread)
 constexpr int GEMV_MAX_CHUNK = 512;              // columns per CTA (x chunk staged in shared memory)
 constexpr int GEMV_T_WARPS = 8;
-constexpr int GEMV_T_SEG = 8192;                 // rows per segment in the T kernel (64 KiB of one column)
+constexpr int GEMV_T_SEG = 2048;                 // rows per (warp, segment) in the T kernel: 16 KiB of one column
 
 // ---- y = A x, A column-major m x n (lda).  grid (ceil(m/256), chunks).  part[chunk*m + r] ----
 __global__ void __launch_bounds__(GEMV_THREADS) gemv_n_kernel(const double* a, long long lda, int m, int n,
@@ -125,7 +125,15 @@ __global__ void __launch_bounds__(256) fold_partials_kernel(const double* part, 
     const int i = blockIdx.x * 256 + threadIdx.x;
     if (i >= len) return;
     double s = nparts > 0 ? part[i] : 0.0;
-    for (int p = 1; p < nparts; ++p) s = __dadd_rn(s, part[(long long)p * len + i]);
+    int p = 1;
+    for (; p + 8 <= nparts; p += 8) {            // loads in flight together, adds in ascending order
+        double v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = part[(long long)(p + u) * len + i];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) s = __dadd_rn(s, v[u]);
+    }
+    for (; p < nparts; ++p) s = __dadd_rn(s, part[(long long)p * len + i]);
     double* o = y + (long long)i * incy;
     *o = accumulate ? __dadd_rn(*o, s) : s;
 }
