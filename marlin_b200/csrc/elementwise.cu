@@ -136,60 +136,101 @@ __global__ void binary_strided_f32_kernel(int op, int rows, int cols, const floa
 // Shared-memory slot of 16B unit (rb, cb, half):  rb*64 + 16*(cb>>3) + 8*half + ((cb&7) ^ (rb&7))
 // which is conflict-free for the column-wise writes and the row-wise reads.
 constexpr int TT = 64;
-// Tiles are visited in 8 x 8 super-tiles (1-D grid, super-tile-major): the CTAs resident at any moment read 4 KiB runs
-// of 8 adjacent tiles per input column and write 4 KiB runs per output column, instead of 512 B pieces 128 KiB apart.
-template <bool SUPER>
+// A CTA owns RM x CM adjacent 64x64 sub-tiles (all loads of the CTA are issued before its single barrier, so RM = 2
+// reads 1 KiB runs per input column and CM = 2 writes 1 KiB runs per output column).  ORDER picks the tile -> CTA map:
+// 0 row-tile fastest (reads walk down the input columns), 1 8x8 super-tiles, 2 column-tile fastest (writes walk down
+// the output columns), 3 diagonal (tc rotated by tr: neither side strides by a power of two between neighbours).
+template <int ORDER, int RM, int CM>
 __global__ void __launch_bounds__(256) transpose_f64_tile_kernel(const double* __restrict__ in, long long ldi,
                                                                 double* __restrict__ out, long long ldo, int rows,
                                                                 int cols, int tiles_r, int tiles_c) {
-    __shared__ double2 tile[32 * 64];
+    extern __shared__ double2 tile_all[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int tr, tc;
-    if (SUPER) {
+    if (ORDER == 1) {
         const int sup_r = (tiles_r + 7) >> 3;
         const int b = blockIdx.x;
         const int sup = b >> 6, inner = b & 63;
         tr = ((sup % sup_r) << 3) + (inner & 7);
         tc = ((sup / sup_r) << 3) + (inner >> 3);
         if (tr >= tiles_r || tc >= tiles_c) return;
+    } else if (ORDER == 2) {
+        tc = blockIdx.x % tiles_c;
+        tr = blockIdx.x / tiles_c;
+    } else if (ORDER == 3) {
+        tr = blockIdx.x % tiles_r;
+        tc = (blockIdx.x / tiles_r + tr) % tiles_c;
+    } else if (ORDER >= 4) {
+        // bands of G tile columns, column-tile fastest inside a band: the CTAs in flight write G*512 B runs per output
+        // column and read long runs per input column
+        constexpr int G = ORDER == 4 ? 16 : (ORDER == 5 ? 32 : 8);
+        const int band = blockIdx.x / (G * tiles_r);
+        const int rem = blockIdx.x - band * (G * tiles_r);
+        const int gw = min(G, tiles_c - band * G);          // last band may be narrower
+        tc = band * G + rem % gw;
+        tr = rem / gw;
     } else {
         tr = blockIdx.x % tiles_r;
         tc = blockIdx.x / tiles_r;
     }
-    const int r0 = tr * TT, c0 = tc * TT;
     // load phase: lane -> micro-row rb, warp -> micro-cols cb = warp + 8*i
-    {
-        const int rb = lane;
-        const int r = r0 + 2 * rb;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int cb = warp + 8 * i;
-            const int c = c0 + 2 * cb;
-            double2 v0 = make_double2(0.0, 0.0), v1 = v0;
-            if (r < rows && c < cols) {   // rows, cols even -> whole micro-block in range
-                v0 = *reinterpret_cast<const double2*>(in + r + (long long)c * ldi);
-                v1 = *reinterpret_cast<const double2*>(in + r + (long long)(c + 1) * ldi);
-            }
-            const int base = rb * 64 + 16 * (cb >> 3) + ((cb & 7) ^ (rb & 7));
-            tile[base] = make_double2(v0.x, v1.x);       // out column r   : in(r, c), in(r, c+1)
-            tile[base + 8] = make_double2(v0.y, v1.y);   // out column r+1 : in(r+1, c), in(r+1, c+1)
-        }
-    }
-    __syncthreads();
-    {
-        const int cb = lane;
-        const int c = c0 + 2 * cb;
+    for (int sr = 0; sr < RM; ++sr)
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int rb = warp + 8 * i;
+        for (int sc = 0; sc < CM; ++sc) {
+            double2* tile = tile_all + (sr * CM + sc) * (32 * 64);
+            const int r0 = (tr * RM + sr) * TT, c0 = (tc * CM + sc) * TT;
+            const int rb = lane;
             const int r = r0 + 2 * rb;
-            if (r < rows && c < cols) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int cb = warp + 8 * i;
+                const int c = c0 + 2 * cb;
+                double2 v0 = make_double2(0.0, 0.0), v1 = v0;
+                if (r < rows && c < cols) {   // rows, cols even -> whole micro-block in range
+                    v0 = *reinterpret_cast<const double2*>(in + r + (long long)c * ldi);
+                    v1 = *reinterpret_cast<const double2*>(in + r + (long long)(c + 1) * ldi);
+                }
                 const int base = rb * 64 + 16 * (cb >> 3) + ((cb & 7) ^ (rb & 7));
-                *reinterpret_cast<double2*>(out + c + (long long)r * ldo) = tile[base];
-                *reinterpret_cast<double2*>(out + c + (long long)(r + 1) * ldo) = tile[base + 8];
+                tile[base] = make_double2(v0.x, v1.x);       // out column r   : in(r, c), in(r, c+1)
+                tile[base + 8] = make_double2(v0.y, v1.y);   // out column r+1 : in(r+1, c), in(r+1, c+1)
             }
         }
+    __syncthreads();
+#pragma unroll
+    for (int sr = 0; sr < RM; ++sr)
+#pragma unroll
+        for (int sc = 0; sc < CM; ++sc) {
+            const double2* tile = tile_all + (sr * CM + sc) * (32 * 64);
+            const int r0 = (tr * RM + sr) * TT, c0 = (tc * CM + sc) * TT;
+            const int cb = lane;
+            const int c = c0 + 2 * cb;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int rb = warp + 8 * i;
+                const int r = r0 + 2 * rb;
+                if (r < rows && c < cols) {
+                    const int base = rb * 64 + 16 * (cb >> 3) + ((cb & 7) ^ (rb & 7));
+                    *reinterpret_cast<double2*>(out + c + (long long)r * ldo) = tile[base];
+                    *reinterpret_cast<double2*>(out + c + (long long)(r + 1) * ldo) = tile[base + 8];
+                }
+            }
+        }
+}
+
+template <int ORDER, int RM, int CM>
+static cudaError_t launch_transpose_f64(const double* in, long long ldi, double* out, long long ldo, int rows, int cols,
+                                        cudaStream_t st) {
+    const int tiles_r = (rows + TT * RM - 1) / (TT * RM), tiles_c = (cols + TT * CM - 1) / (TT * CM);
+    const int smem = RM * CM * 32 * 64 * (int)sizeof(double2);
+    auto kern = transpose_f64_tile_kernel<ORDER, RM, CM>;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
     }
+    const int grid = ORDER == 1 ? ((tiles_r + 7) / 8) * ((tiles_c + 7) / 8) * 64 : tiles_r * tiles_c;
+    kern<<<grid, 256, smem, st>>>(in, ldi, out, ldo, rows, cols, tiles_r, tiles_c);
+    return cudaGetLastError();
 }
 
 // generic transpose (any alignment / odd sizes / any element type): 32x32 tile, scalar accesses
@@ -303,8 +344,7 @@ __device__ __forceinline__ unsigned long long xs_step(unsigned long long s) {
     s ^= s << 4;
     return s;
 }
-constexpr int FILL_CHUNK = 16;   // values per thread (256 x 17 x 8 B = 34 KiB of static smem)
-__device__ unsigned long long g_jump[40][64];      // same tables in global memory: lane-parallel (coalesced) access
+__device__ unsigned long long g_jump[40][64];      // columns of T^(2^j), j = 0..39 (global memory: lane-parallel access)
 
 // T^steps * s computed by a whole warp: lane l owns columns l and l+32 of each power-of-two matrix, the partial XORs
 // are combined with shuffles.  ~25 instructions per set bit of `steps` instead of a 64-iteration serial loop.
@@ -321,62 +361,93 @@ __device__ __forceinline__ unsigned long long xs_jump_warp(unsigned long long s,
     return s;
 }
 
-// Block = 256 threads; thread (warp w, lane l) generates FILL_CHUNK consecutive values starting at value
-// block_first + (32 w + l) * FILL_CHUNK.  Jump = block base (warp-parallel) + warp part (warp-parallel)
-// + lane part (<= 5 serial levels from shared-memory tables), then coalesced write-out through shared memory.
-constexpr int FILL_LANE_LO = 5;     // lane offset = l * 2 * FILL_CHUNK steps = l << 5 : table levels 5..9
+// One CTA = 256 threads x FILL_PER_THREAD consecutive values (512 KiB of output).  Thread t owns values
+// [block_first + t*FILL_PER_THREAD, +FILL_PER_THREAD): long per-thread runs amortise the jump-ahead (one CTA-base jump by
+// warp 0, a 3-level warp part done cooperatively, a <= 5-level lane part done serially, all from shared-memory tables),
+// and the values go out in rounds of FILL_ROUND per thread through a padded shared-memory stage so that every store
+// instruction writes whole 128-byte lines.
+constexpr int FILL_PER_THREAD = 256;
+constexpr int FILL_ROUND = 16;
+constexpr int FILL_LVL0 = 9;        // thread offset = t * 2 * FILL_PER_THREAD steps = t << 9: table levels 9..16
 __global__ void __launch_bounds__(256) fill_uniform_kernel(double* out, long long rs, long long cs, int rows, int cols,
                                                           int row_major, unsigned long long state0, long long first,
                                                           double lo, double hi) {
-    __shared__ double stage[256][FILL_CHUNK + 1];
-    __shared__ unsigned long long jump_s[5][64];
+    __shared__ double stage[256][FILL_ROUND + 1];
+    __shared__ unsigned long long jump_s[8][64];
+    __shared__ unsigned long long base_s;
     const long long total = (long long)rows * cols;
-    const long long block_first = (long long)blockIdx.x * 256 * FILL_CHUNK;
+    const long long block_first = (long long)blockIdx.x * 256 * FILL_PER_THREAD;
     if (block_first >= total) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int e = threadIdx.x; e < 5 * 64; e += 256) jump_s[e >> 6][e & 63] = g_jump[FILL_LANE_LO + (e >> 6)][e & 63];
-    // every warp: base jump to its own first value (block base + 32 * warp chunks), cooperatively
-    unsigned long long s = xs_jump_warp(state0, 2ull * (unsigned long long)(first + block_first + (long long)warp * 32 * FILL_CHUNK), lane);
-    __syncthreads();
-    const long long i0 = block_first + (long long)threadIdx.x * FILL_CHUNK;
-    const double span = __dsub_rn(hi, lo);
-    if (i0 < total) {
-        unsigned steps = lane;                     // in units of 2^FILL_LANE_LO xorshift steps
-#pragma unroll 1
-        for (int j = 0; j < 5 && steps; ++j, steps >>= 1) {
-            if (steps & 1u) {
-                unsigned long long t = 0, x = s;
-                while (x) {
-                    t ^= jump_s[j][__ffsll((long long)x) - 1];
-                    x &= x - 1;
-                }
-                s = t;
-            }
-        }
-        const int cnt = (int)min((long long)FILL_CHUNK, total - i0);
-        for (int v = 0; v < cnt; ++v) {
-            s = xs_step(s);
-            const unsigned long long hi26 = s & ((1ull << 26) - 1);
-            s = xs_step(s);
-            const unsigned long long lo27 = s & ((1ull << 27) - 1);
-            const double u = (double)((hi26 << 27) + lo27) * 0x1.0p-53;
-            stage[threadIdx.x][v] = __dadd_rn(__dmul_rn(span, u), lo);
-        }
+    for (int e = threadIdx.x; e < 8 * 64; e += 256) jump_s[e >> 6][e & 63] = g_jump[FILL_LVL0 + (e >> 6)][e & 63];
+    if (warp == 0) {
+        const unsigned long long b = xs_jump_warp(state0, 2ull * (unsigned long long)(first + block_first), lane);
+        if (lane == 0) base_s = b;
     }
     __syncthreads();
-    const int block_cnt = (int)min((long long)256 * FILL_CHUNK, total - block_first);
+    unsigned long long s = base_s;
+    // warp part: bits 5..7 of the thread index -> levels FILL_LVL0+5 .. +7, one matrix-vector product per set bit by the
+    // whole warp (lane l owns columns l and l+32)
+#pragma unroll
+    for (int j = 5; j < 8; ++j) {
+        if ((warp >> (j - 5)) & 1) {
+            unsigned long long v = ((s >> lane) & 1ull) ? jump_s[j][lane] : 0ull;
+            v ^= ((s >> (lane + 32)) & 1ull) ? jump_s[j][lane + 32] : 0ull;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v ^= __shfl_xor_sync(0xffffffffu, v, o);
+            s = v;
+        }
+    }
+    // lane part: bits 0..4 -> levels FILL_LVL0 .. +4, serial (every lane has its own vector by now)
+#pragma unroll 1
+    for (int j = 0; j < 5; ++j) {
+        if ((lane >> j) & 1) {
+            unsigned long long t = 0, x = s;
+            while (x) {
+                t ^= jump_s[j][__ffsll((long long)x) - 1];
+                x &= x - 1;
+            }
+            s = t;
+        }
+    }
+    const long long i0 = block_first + (long long)threadIdx.x * FILL_PER_THREAD;
+    const double span = __dsub_rn(hi, lo);
     // storage contiguous in fill order (a row-major shard filled row-major, or a packed column-major block filled
     // column-major): linear index == storage index, no 64-bit divisions on the store path
     const bool linear = row_major ? (cs == 1 && rs == cols) : (rs == 1 && cs == rows);
-    if (linear) {
-        for (int e = threadIdx.x; e < block_cnt; e += 256) out[block_first + e] = stage[e / FILL_CHUNK][e % FILL_CHUNK];
-    } else {
-        for (int e = threadIdx.x; e < block_cnt; e += 256) {
-            const long long i = block_first + e;
-            long long r, c;
-            if (row_major) { r = i / cols; c = i - r * cols; } else { c = i / rows; r = i - c * rows; }
-            out[r * rs + c * cs] = stage[e / FILL_CHUNK][e % FILL_CHUNK];
+    const long long block_end = min(total, block_first + 256ll * FILL_PER_THREAD);
+#pragma unroll 1
+    for (int round = 0; round < FILL_PER_THREAD / FILL_ROUND; ++round) {
+        if (block_first + (long long)round * FILL_ROUND >= block_end) break;      // uniform: nothing left for any thread
+        if (i0 + (long long)round * FILL_ROUND < total) {
+#pragma unroll
+            for (int v = 0; v < FILL_ROUND; ++v) {
+                s = xs_step(s);
+                const unsigned long long hi26 = s & ((1ull << 26) - 1);
+                s = xs_step(s);
+                const unsigned long long lo27 = s & ((1ull << 27) - 1);
+                const double u = (double)((hi26 << 27) + lo27) * 0x1.0p-53;
+                stage[threadIdx.x][v] = __dadd_rn(__dmul_rn(span, u), lo);
+            }
         }
+        __syncthreads();
+        // element e of the round: owner thread e / FILL_ROUND, its value j = e % FILL_ROUND -> 16 consecutive lanes
+        // write one 128-byte line
+#pragma unroll 4
+        for (int e = threadIdx.x; e < 256 * FILL_ROUND; e += 256) {
+            const int owner = e / FILL_ROUND, j = e % FILL_ROUND;
+            const long long i = block_first + (long long)owner * FILL_PER_THREAD + round * FILL_ROUND + j;
+            if (i < total) {
+                if (linear) {
+                    out[i] = stage[owner][j];
+                } else {
+                    long long r, c;
+                    if (row_major) { r = i / cols; c = i - r * cols; } else { c = i / rows; r = i - c * rows; }
+                    out[r * rs + c * cs] = stage[owner][j];
+                }
+            }
+        }
+        __syncthreads();
     }
 }
 
@@ -447,14 +518,26 @@ cudaError_t transpose_f64(const double* in, long long ldi, double* out, long lon
     const bool fast = (rows % 2 == 0) && (cols % 2 == 0) && (ldi % 2 == 0) && (ldo % 2 == 0) &&
                       (((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) == 0);
     if (fast) {
-        const int tiles_r = (rows + TT - 1) / TT, tiles_c = (cols + TT - 1) / TT;
         static int variant = -1;
-        if (variant < 0) { const char* ev = getenv("MARLIN_B200_TRANSPOSE_VARIANT"); variant = ev ? atoi(ev) : 0; }   // measured: the super-tile order (1) is ~1.5 % slower than the plain order (0)
-        if (variant == 1) {
-            const int sup = ((tiles_r + 7) / 8) * ((tiles_c + 7) / 8);
-            transpose_f64_tile_kernel<true><<<sup * 64, 256, 0, st>>>(in, ldi, out, ldo, rows, cols, tiles_r, tiles_c);
-        } else {
-            transpose_f64_tile_kernel<false><<<tiles_r * tiles_c, 256, 0, st>>>(in, ldi, out, ldo, rows, cols, tiles_r, tiles_c);
+        if (variant < 0) { const char* ev = getenv("MARLIN_B200_TRANSPOSE_VARIANT"); variant = ev ? atoi(ev) : 0; }
+        switch (variant) {
+            case 1: return launch_transpose_f64<1, 1, 1>(in, ldi, out, ldo, rows, cols, st);
+            case 2: return launch_transpose_f64<2, 1, 1>(in, ldi, out, ldo, rows, cols, st);
+            case 3: return launch_transpose_f64<3, 1, 1>(in, ldi, out, ldo, rows, cols, st);
+            case 4: return launch_transpose_f64<0, 2, 1>(in, ldi, out, ldo, rows, cols, st);
+            case 5: return launch_transpose_f64<0, 1, 2>(in, ldi, out, ldo, rows, cols, st);
+            case 6: return launch_transpose_f64<2, 1, 2>(in, ldi, out, ldo, rows, cols, st);
+            case 7: return launch_transpose_f64<3, 2, 1>(in, ldi, out, ldo, rows, cols, st);
+            case 8: return launch_transpose_f64<3, 1, 2>(in, ldi, out, ldo, rows, cols, st);
+            case 9: return launch_transpose_f64<0, 2, 2>(in, ldi, out, ldo, rows, cols, st);
+            case 10: return launch_transpose_f64<2, 2, 1>(in, ldi, out, ldo, rows, cols, st);
+            case 11: return launch_transpose_f64<4, 1, 1>(in, ldi, out, ldo, rows, cols, st);
+            case 12: return launch_transpose_f64<4, 2, 1>(in, ldi, out, ldo, rows, cols, st);
+            case 13: return launch_transpose_f64<5, 1, 1>(in, ldi, out, ldo, rows, cols, st);
+            case 14: return launch_transpose_f64<5, 2, 1>(in, ldi, out, ldo, rows, cols, st);
+            case 15: return launch_transpose_f64<6, 1, 1>(in, ldi, out, ldo, rows, cols, st);
+            case 16: return launch_transpose_f64<6, 2, 1>(in, ldi, out, ldo, rows, cols, st);
+            default: return launch_transpose_f64<0, 1, 1>(in, ldi, out, ldo, rows, cols, st);
         }
     } else {
         dim3 grid((rows + 31) / 32, (cols + 31) / 32);
@@ -552,7 +635,7 @@ cudaError_t fill_uniform_f64(double* out, long long rs, long long cs, int rows, 
     cudaError_t e = fill_uniform_init_tables();
     if (e != cudaSuccess) return e;
     const long long total = (long long)rows * cols;
-    const long long per_block = 256ll * FILL_CHUNK;
+    const long long per_block = 256ll * FILL_PER_THREAD;
     const int blocks = (int)((total + per_block - 1) / per_block);
     fill_uniform_kernel<<<blocks, 256, 0, st>>>(out, rs, cs, rows, cols, row_major, state0, first, lo, hi);
     return cudaGetLastError();

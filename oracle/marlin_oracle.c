@@ -226,6 +226,19 @@ void mo_uniform_fill(int64_t partition_seed, long first, long n, double lo, doub
     }
 }
 
+/* The same stream continued from an explicit XORShift state (test helper: lets the Python side skip ahead with its own
+ * GF(2) matrix power instead of stepping 2*first times). */
+void mo_uniform_fill_from_state(uint64_t state, long n, double lo, double hi, double* out) {
+    uint64_t s = state;
+    const double span = hi - lo;
+    for (long i = 0; i < n; ++i) {
+        const int64_t a = xs_next(&s, 26);
+        const int64_t b = xs_next(&s, 27);
+        const double u = (double)((a << 27) + b) * 0x1.0p-53;
+        out[i] = span * u + lo;
+    }
+}
+
 /* java.util.Random(seed): successive nextLong() — the partition seeds of rdd/RandomRDD.scala:28-45 */
 void mo_java_random_longs(int64_t seed, int n, int64_t* out) {
     const uint64_t mask = (1ull << 48) - 1;

@@ -60,6 +60,7 @@ def clib() -> C.CDLL:
         lib.mo_hash_seed.restype = C.c_int64
         lib.mo_hash_seed.argtypes = [C.c_int64]
         lib.mo_uniform_fill.argtypes = [C.c_int64, C.c_long, C.c_long, C.c_double, C.c_double, dp]
+        lib.mo_uniform_fill_from_state.argtypes = [C.c_uint64, C.c_long, C.c_double, C.c_double, dp]
         lib.mo_java_random_longs.argtypes = [C.c_int64, C.c_int, C.POINTER(C.c_int64)]
         lib.mo_split_method.argtypes = [C.c_int64, C.c_int64, C.c_int64, C.c_int, C.POINTER(C.c_int)]
         _lib = lib
@@ -224,6 +225,47 @@ def uniform_stream(partition_seed: int, first: int, n: int, lo: float = 0.0, hi:
     out = np.empty(n)
     if n:
         clib().mo_uniform_fill(partition_seed, first, n, lo, hi, _dp(out))
+    return out
+
+
+_M64 = (1 << 64) - 1
+
+
+def _xs_step(s: int) -> int:
+    """XORShiftRandom.next's state update (utils/RandomDataGenerator.scala:121-127) on a Python int."""
+    s ^= (s << 21) & _M64
+    s ^= s >> 35
+    s ^= (s << 4) & _M64
+    return s
+
+
+def xorshift_jump(state: int, steps: int) -> int:
+    """state after `steps` updates, by square-and-multiply on the 64x64 GF(2) matrix of the (linear) update —
+    an independent check of the device kernel's jump-ahead tables."""
+    def apply(cols, v):
+        out, b = 0, 0
+        while v:
+            if v & 1:
+                out ^= cols[b]
+            v >>= 1
+            b += 1
+        return out
+    power = [_xs_step(1 << b) for b in range(64)]           # columns of T
+    while steps:
+        if steps & 1:
+            state = apply(power, state)
+        steps >>= 1
+        if steps:
+            power = [apply(power, c) for c in power]         # T^(2k) = T^k . T^k
+    return state
+
+
+def uniform_stream_far(partition_seed: int, first: int, n: int, lo: float = 0.0, hi: float = 1.0) -> np.ndarray:
+    """uniform_stream for offsets too far to step through: jump 2*first updates, then generate sequentially."""
+    state = xorshift_jump(hash_seed(partition_seed) & _M64, 2 * first)
+    out = np.empty(n)
+    if n:
+        clib().mo_uniform_fill_from_state(state, n, lo, hi, _dp(out))
     return out
 
 

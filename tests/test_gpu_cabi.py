@@ -311,6 +311,31 @@ def test_fill_uniform_bit_exact_with_oracle_stream(gpu, oracle, row_major):
     assert np.array_equal(download(gpu, h, rows, cols), ref)
 
 
+@pytest.mark.parametrize("row_major", [0, 1])
+def test_fill_uniform_many_ctas_and_far_offsets(gpu, oracle, row_major):
+    """Several CTAs with a ragged tail (every thread owns a long run and jumps to it), stream offsets beyond 2^33, and a
+    strided destination (slice of a larger block) that takes the non-linear store path."""
+    lib, ctx = gpu
+    rows, cols = 701, 613                                   # 429,713 values: 6 full CTAs of 65,536 + a partial one
+    h = alloc(gpu, rows, cols)
+    for seed, first in ((2024, 0), (-7, (1 << 33) + 12345), (31, (1 << 38) - 3)):
+        nat.check(lib.mb_fill_uniform(ctx, h, seed, first, 0.0, 1.0, row_major))
+        stream = oracle.uniform_stream_far(seed, first, rows * cols)      # independent GF(2) matrix power, then sequential
+        ref = stream.reshape(rows, cols) if row_major else stream.reshape((rows, cols), order="F")
+        assert np.array_equal(download(gpu, h, rows, cols), ref)
+    big = alloc(gpu, rows + 9, cols + 5)
+    nat.check(lib.mb_block_fill(ctx, big, -1.0))
+    view = nat.c_blk()
+    nat.check(lib.mb_block_slice(ctx, big, 4, 4 + rows, 2, 2 + cols, C.byref(view)))
+    nat.check(lib.mb_fill_uniform(ctx, view, 99, 77, 0.0, 1.0, row_major))
+    stream = oracle.uniform_stream(99, 77, rows * cols)
+    ref = stream.reshape(rows, cols) if row_major else stream.reshape((rows, cols), order="F")
+    full = download(gpu, big, rows + 9, cols + 5)
+    assert np.array_equal(full[4:4 + rows, 2:2 + cols], ref)
+    full[4:4 + rows, 2:2 + cols] = -1.0
+    assert np.all(full == -1.0)                             # nothing written outside the view
+
+
 def test_matmul_blocked_seq_order(gpu, oracle):
     """mb_matmul_blocked == BlockMatrix.multiply (BlockMatrix.scala:149-186) for a ragged (3,2,2) grid."""
     lib, ctx = gpu

@@ -234,3 +234,14 @@ def test_matrix_vector(oracle):                           # BlockMatrix.scala:24
         y = oracle.block_multiply_vector(arr, xx)
         assert np.abs(y - A @ xx).max() <= 1e-13
     assert abs(oracle.vector_dot(xx, xx) - float(xx @ xx)) <= 1e-13
+
+
+def test_xorshift_jump_equals_stepping(oracle):
+    """The oracle's own skip-ahead (GF(2) matrix power) against plain stepping — it checks the device jump tables."""
+    for seed, first in ((5, 0), (123456789, 1000), (-42, 123457)):
+        assert np.array_equal(oracle.uniform_stream(seed, first, 40), oracle.uniform_stream_far(seed, first, 40))
+    s = 0x9E3779B97F4A7C15
+    t = s
+    for _ in range(777):
+        t = oracle._xs_step(t)
+    assert oracle.xorshift_jump(s, 777) == t
