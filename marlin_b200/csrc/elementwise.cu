@@ -519,8 +519,12 @@ cudaError_t transpose_f64(const double* in, long long ldi, double* out, long lon
                       (((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) == 0);
     if (fast) {
         static int variant = -1;
-        if (variant < 0) { const char* ev = getenv("MARLIN_B200_TRANSPOSE_VARIANT"); variant = ev ? atoi(ev) : 0; }
+        // measured on B200 at 16384^2 (scripts/bench_transpose.py, profiles/r01_transpose_sweep.json): 0 = 5.73 TB/s,
+        // 2 = 6.00, 12 = 6.03, 16 = 6.08 (default): what matters is that the CTAs in flight write long runs per
+        // output column (column-tile-fastest maps) and that a CTA reads 1 KiB per input column (RM = 2)
+        if (variant < 0) { const char* ev = getenv("MARLIN_B200_TRANSPOSE_VARIANT"); variant = ev ? atoi(ev) : 16; }
         switch (variant) {
+            case 0: return launch_transpose_f64<0, 1, 1>(in, ldi, out, ldo, rows, cols, st);
             case 1: return launch_transpose_f64<1, 1, 1>(in, ldi, out, ldo, rows, cols, st);
             case 2: return launch_transpose_f64<2, 1, 1>(in, ldi, out, ldo, rows, cols, st);
             case 3: return launch_transpose_f64<3, 1, 1>(in, ldi, out, ldo, rows, cols, st);
@@ -537,7 +541,7 @@ cudaError_t transpose_f64(const double* in, long long ldi, double* out, long lon
             case 14: return launch_transpose_f64<5, 2, 1>(in, ldi, out, ldo, rows, cols, st);
             case 15: return launch_transpose_f64<6, 1, 1>(in, ldi, out, ldo, rows, cols, st);
             case 16: return launch_transpose_f64<6, 2, 1>(in, ldi, out, ldo, rows, cols, st);
-            default: return launch_transpose_f64<0, 1, 1>(in, ldi, out, ldo, rows, cols, st);
+            default: return launch_transpose_f64<6, 2, 1>(in, ldi, out, ldo, rows, cols, st);
         }
     } else {
         dim3 grid((rows + 31) / 32, (cols + 31) / 32);
