@@ -718,6 +718,42 @@ int32_t mb_matmul_blocked_host(mb_ctx* ctx, const double* const* A_host, const d
             for (int kk = 0; kk < k && e == cudaSuccess && rc == MB_OK; ++kk) {
                 const bool first_product = (i == 0 && j == 0 && kk == 0);
                 const bool last_product = (i == m - 1 && j == n - 1 && kk == k - 1);
+                if (first_product && !last_product && k_len[kk] >= 1024 && row_len[i] > 0 && col_len[j] > 0) {
+                    // The first product is split along K: the GEMM on chunk q needs only columns [k0,k1) of A and rows
+                    // [k0,k1) of B, so the tensor cores start after a quarter of each tile has crossed PCIe and the rest
+                    // of both uploads hides behind the partial products (accumulated in place, beta = 1).
+                    const int nk = 4;
+                    const int lda8 = even(row_len[i]), ldb8 = even(k_len[kk]);
+                    for (int q = 0; q < nk && e == cudaSuccess && rc == MB_OK; ++q) {
+                        const int k0 = q == 0 ? 0 : (int)(((long long)k_len[kk] * q / nk) & ~15ll);
+                        const int k1 = q == nk - 1 ? k_len[kk] : (int)(((long long)k_len[kk] * (q + 1) / nk) & ~15ll);
+                        cudaEvent_t ev = nullptr;
+                        e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+                        if (e != cudaSuccess) break;
+                        chunk_events.push_back(ev);
+                        e = cudaMemcpy2DAsync(base + offA[i * k + kk] + (size_t)k0 * lda8 * 8, (size_t)lda8 * 8,
+                                              A_host[i * k + kk] + (size_t)k0 * row_len[i], (size_t)row_len[i] * 8,
+                                              (size_t)row_len[i] * 8, k1 - k0, cudaMemcpyHostToDevice, ctx->h2d_stream);
+                        if (e == cudaSuccess)
+                            e = cudaMemcpy2DAsync(base + offB[kk * n + j] + (size_t)k0 * 8, (size_t)ldb8 * 8, B_host[kk * n + j] + k0,
+                                                  (size_t)k_len[kk] * 8, (size_t)(k1 - k0) * 8, col_len[j], cudaMemcpyHostToDevice,
+                                                  ctx->h2d_stream);
+                        if (e == cudaSuccess) e = cudaEventRecord(ev, ctx->h2d_stream);
+                        if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->stream, ev, 0);
+                        if (e != cudaSuccess) break;
+                        rc = dgemm_device_impl(ctx, 'N', 'N', row_len[i], col_len[j], k1 - k0, 1.0,
+                                               reinterpret_cast<double*>(base + offA[i * k + kk]) + (size_t)k0 * lda8, lda8,
+                                               reinterpret_cast<double*>(base + offB[kk * n + j]) + k0, ldb8, (kk > 0 || q > 0) ? 1.0 : 0.0,
+                                               reinterpret_cast<double*>(base + offC[i * n + j]), lda8, false);
+                    }
+                    if (e != cudaSuccess || rc != MB_OK) break;
+                    // later users of these two tiles wait for the whole of them
+                    e = cudaEventCreateWithFlags(&evA[i * k + kk], cudaEventDisableTiming);
+                    if (e == cudaSuccess) e = cudaEventRecord(evA[i * k + kk], ctx->h2d_stream);
+                    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&evB[kk * n + j], cudaEventDisableTiming);
+                    if (e == cudaSuccess) e = cudaEventRecord(evB[kk * n + j], ctx->h2d_stream);
+                    continue;
+                }
                 const int nch = ((first_product || last_product) && col_len[j] >= 1024) ? 4 : 1;
                 // uploads in first-use order (seq = i*n*k + j*k + kk)
                 upload(true, i * k + kk, row_len[i], k_len[kk], A_host[i * k + kk], offA[i * k + kk], evA[i * k + kk]);

@@ -359,10 +359,12 @@ def test_matmul_blocked_seq_order(gpu, oracle):
             assert np.abs(got - refb[(i, j)]).max() <= 1e-12
 
 
-@pytest.mark.parametrize("dims", [(75, 64, 51, 2, 3, 2), (300, 200, 2100, 1, 2, 2), (260, 130, 1100, 1, 1, 1)])
+@pytest.mark.parametrize("dims", [(75, 64, 51, 2, 3, 2), (300, 200, 2100, 1, 2, 2), (260, 130, 1100, 1, 1, 1),
+                                  (200, 2300, 260, 1, 2, 2), (131, 2111, 77, 2, 2, 1), (140, 1200, 1300, 2, 1, 2)])
 def test_matmul_blocked_host_pipelined(gpu, oracle, dims):
     """mb_matmul_blocked_host: host tiles in, host tiles out (pipelined H2D / DMMA / D2H) == BlockMatrix.multiply.
-    Column counts >= 1024 exercise the chunked first product (B uploaded in quarters) and chunked last download."""
+    Column counts >= 1024 exercise the chunked last download (and, for a single product, the column-chunked upload of
+    B); K extents >= 1024 exercise the K-chunked first product (quarters of A and B uploaded and multiplied in turn)."""
     lib, ctx = gpu
     rng = np.random.default_rng(12)
     M, K, N, m, k, n = dims
