@@ -197,24 +197,25 @@ __global__ void __launch_bounds__(256) transpose_f64_tile_kernel(const double* _
             }
         }
     __syncthreads();
+    // store phase: the CM sub-tiles of one output column are written back to back (CM * 512 B runs)
 #pragma unroll
     for (int sr = 0; sr < RM; ++sr)
 #pragma unroll
-        for (int sc = 0; sc < CM; ++sc) {
-            const double2* tile = tile_all + (sr * CM + sc) * (32 * 64);
-            const int r0 = (tr * RM + sr) * TT, c0 = (tc * CM + sc) * TT;
-            const int cb = lane;
-            const int c = c0 + 2 * cb;
+        for (int i = 0; i < 4; ++i) {
+            const int rb = warp + 8 * i;
+            const int r = (tr * RM + sr) * TT + 2 * rb;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int rb = warp + 8 * i;
-                const int r = r0 + 2 * rb;
-                if (r < rows && c < cols) {
-                    const int base = rb * 64 + 16 * (cb >> 3) + ((cb & 7) ^ (rb & 7));
-                    *reinterpret_cast<double2*>(out + c + (long long)r * ldo) = tile[base];
-                    *reinterpret_cast<double2*>(out + c + (long long)(r + 1) * ldo) = tile[base + 8];
+            for (int half = 0; half < 2; ++half)
+#pragma unroll
+                for (int sc = 0; sc < CM; ++sc) {
+                    const double2* tile = tile_all + (sr * CM + sc) * (32 * 64);
+                    const int cb = lane;
+                    const int c = (tc * CM + sc) * TT + 2 * cb;
+                    if (r < rows && c < cols) {
+                        const int base = rb * 64 + 16 * (cb >> 3) + ((cb & 7) ^ (rb & 7));
+                        *reinterpret_cast<double2*>(out + c + (long long)(r + half) * ldo) = tile[base + 8 * half];
+                    }
                 }
-            }
         }
 }
 
@@ -541,6 +542,9 @@ cudaError_t transpose_f64(const double* in, long long ldi, double* out, long lon
             case 14: return launch_transpose_f64<5, 2, 1>(in, ldi, out, ldo, rows, cols, st);
             case 15: return launch_transpose_f64<6, 1, 1>(in, ldi, out, ldo, rows, cols, st);
             case 16: return launch_transpose_f64<6, 2, 1>(in, ldi, out, ldo, rows, cols, st);
+            case 17: return launch_transpose_f64<6, 1, 2>(in, ldi, out, ldo, rows, cols, st);
+            case 18: return launch_transpose_f64<2, 1, 2>(in, ldi, out, ldo, rows, cols, st);
+            case 19: return launch_transpose_f64<4, 1, 2>(in, ldi, out, ldo, rows, cols, st);
             default: return launch_transpose_f64<6, 2, 1>(in, ldi, out, ldo, rows, cols, st);
         }
     } else {
