@@ -204,6 +204,16 @@ int32_t mb_matmul_blocked_host(mb_ctx* ctx, const double* const* A_host, const d
                                int32_t m, int32_t k, int32_t n, const int32_t* row_len, const int32_t* k_len,
                                const int32_t* col_len, double* const* C_host);
 
+/* a5: DenseVecMatrix.multiply(B: BDM[Double]) (matrix/DenseVecMatrix.scala:1660-1680) for the row shard one process
+ * holds: C_rows = A_rows * B.  A_rows / C_rows are row-major shards (transposed views of the column-major array
+ * underneath), B is the broadcast matrix; the rows never change GPU, so N ranks run N independent calls. */
+int32_t mb_matmul_rowsharded(mb_ctx* ctx, const mb_block* A_rows, const mb_block* B, mb_block* C_rows);
+/* The same for JVM-held rows: A_host = the shard's rows back to back (row-major, k doubles per row: the packed
+ * `rowsMat` of :1672-1675), B_host = column-major k x n, C_host receives rows x n row-major.  Row chunks of ~256 MiB
+ * are pipelined over three streams (H2D of chunk c+1, the DMMA product of chunk c, D2H of chunk c-1). */
+int32_t mb_matmul_rowsharded_host(mb_ctx* ctx, const double* A_host, int64_t rows, int32_t k, const double* B_host,
+                                  int32_t n, double* C_host);
+
 /* ---- peer memory: NVLink P2P between the per-GPU processes of one box (CUDA IPC) ------------------------------
  * Replaces the shuffle transport of the multiply (matrix/BlockMatrix.scala:161-177): a rank maps the tile buffers
  * of the others once, pulls the tiles it needs with copy-engine DMA (mb_memcpy_async on a side stream) and lets its

@@ -80,6 +80,8 @@ SIGNATURES = {
     "mb_block_len": (c_i32, [c_i64, c_i32, C.POINTER(c_i32), C.POINTER(c_i32)]),
     "mb_matmul_blocked_host": (c_i32, [c_ctx, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), c_i32, c_i32, c_i32,
                                        C.POINTER(c_i32), C.POINTER(c_i32), C.POINTER(c_i32), C.POINTER(C.c_void_p)]),
+    "mb_matmul_rowsharded": (c_i32, [c_ctx, c_blk, c_blk, c_blk]),
+    "mb_matmul_rowsharded_host": (c_i32, [c_ctx, C.c_void_p, c_i64, c_i32, C.c_void_p, c_i32, C.c_void_p]),
     "mb_ipc_export": (c_i32, [c_ctx, C.c_void_p, C.c_char_p, C.POINTER(c_i64), C.POINTER(c_i64)]),
     "mb_ipc_open": (c_i32, [c_ctx, C.c_char_p, C.POINTER(C.c_void_p)]),
     "mb_ipc_close_all": (c_i32, [c_ctx]),

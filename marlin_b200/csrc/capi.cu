@@ -11,6 +11,7 @@
 #include <cuda_runtime.h>
 #include <algorithm>
 #include <cstdarg>
+#include <cstdlib>
 #include <cstdio>
 #include <cstring>
 #include <new>
@@ -835,6 +836,106 @@ int32_t mb_matmul_blocked_host(mb_ctx* ctx, const double* const* A_host, const d
     if (ev_done) cudaEventDestroy(ev_done);
     if (rc != MB_OK) return rc;
     if (e != cudaSuccess) return cuda_fail(e, "mb_matmul_blocked_host");
+    return MB_OK;
+}
+
+// DenseVecMatrix.multiply(B: BDM) for one row shard (matrix/DenseVecMatrix.scala:1660-1680): C_rows = A_rows * B with
+// A_rows / C_rows row-major shards (transposed views) and B the broadcast matrix.
+int32_t mb_matmul_rowsharded(mb_ctx* ctx, const mb_block* A_rows, const mb_block* B, mb_block* C_rows) {
+    MB_CTX(ctx);
+    if (!A_rows || !B || !C_rows) return fail(MB_ERR_INVALID_ARG, "mb_matmul_rowsharded: null block");
+    if (A_rows->cols != B->rows)
+        return fail(MB_ERR_DIM_MISMATCH, "Dimension mismatch during matrix-matrix multiplication: %d vs %d", A_rows->cols, B->rows);
+    return mb_block_gemm(ctx, A_rows, B, C_rows, 0);
+}
+
+// The same for JVM-held rows: A_host is the shard's rows back to back (row-major, each row k doubles — exactly the
+// `Array[Double]` a partition's rows are packed into at :1672-1675), B_host the column-major k x n broadcast matrix,
+// C_host receives the row-major rows x n result.  Row chunks are pipelined: H2D of chunk c+1, the DMMA product of chunk
+// c (C^T = B^T * A^T on the row-major data, no transposition pass) and D2H of chunk c-1 run on three streams over a
+// ring of three device slots.
+int32_t mb_matmul_rowsharded_host(mb_ctx* ctx, const double* A_host, int64_t rows, int32_t k, const double* B_host,
+                                  int32_t n, double* C_host) {
+    MB_CTX(ctx);
+    if (rows < 0 || k < 0 || n < 0 || (rows > 0 && ((k > 0 && !A_host) || (n > 0 && !C_host))) || (k > 0 && n > 0 && !B_host))
+        return fail(MB_ERR_INVALID_ARG, "mb_matmul_rowsharded_host: bad argument");
+    if (rows == 0 || n == 0) return MB_OK;
+    if (!ctx->h2d_stream) {
+        MB_CUDA(cudaStreamCreateWithFlags(&ctx->h2d_stream, cudaStreamNonBlocking));
+        MB_CUDA(cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking));
+    }
+    constexpr int SLOTS = 3;
+    // ~256 MiB of A (or C, whichever is wider) per chunk, a multiple of 128 rows (whole GEMM tiles), at least one tile;
+    // MARLIN_B200_ROWSHARD_CHUNK_MIB overrides the size (the tests use it to run many chunks on small inputs)
+    long long chunk_mib = 256;
+    if (const char* ev = getenv("MARLIN_B200_ROWSHARD_CHUNK_MIB")) chunk_mib = std::max(1, atoi(ev));
+    long long chunk = (chunk_mib << 20) / (8ll * std::max(std::max(k, n), 1));
+    chunk = std::max(128ll, chunk / 128 * 128);
+    chunk = std::min<long long>(chunk, (rows + 127) / 128 * 128);
+    const int kk = std::max(k, 1);
+    auto slot = [](size_t bytes) { return (bytes + 255) & ~size_t(255); };
+    const size_t bytesB = slot((size_t)kk * n * 8), bytesA = slot((size_t)chunk * kk * 8), bytesC = slot((size_t)chunk * n * 8);
+    const size_t total = bytesB + SLOTS * (bytesA + bytesC);
+    if (total > ctx->workspace_bytes) {
+        if (ctx->workspace) { MB_CUDA(cudaDeviceSynchronize()); cudaFree(ctx->workspace); ctx->workspace = nullptr; ctx->workspace_bytes = 0; }
+        MB_CUDA(cudaMalloc(&ctx->workspace, total));
+        ctx->workspace_bytes = total;
+    }
+    char* base = static_cast<char*>(ctx->workspace);
+    double* dB = reinterpret_cast<double*>(base);
+    auto dA = [&](int s_) { return reinterpret_cast<double*>(base + bytesB + (size_t)s_ * (bytesA + bytesC)); };
+    auto dC = [&](int s_) { return reinterpret_cast<double*>(base + bytesB + (size_t)s_ * (bytesA + bytesC) + bytesA); };
+    cudaEvent_t ev_start = nullptr, ev_b = nullptr, ev_up[SLOTS] = {}, ev_gemm[SLOTS] = {}, ev_down[SLOTS] = {};
+    cudaError_t e = cudaSuccess;
+    int32_t rc = MB_OK;
+    auto mk = [&](cudaEvent_t& ev) { if (e == cudaSuccess && !ev) e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming); };
+    mk(ev_start); mk(ev_b);
+    for (int s_ = 0; s_ < SLOTS; ++s_) { mk(ev_up[s_]); mk(ev_gemm[s_]); mk(ev_down[s_]); }
+    // the workspace may still be in use by an earlier call on ctx->stream
+    if (e == cudaSuccess) e = cudaEventRecord(ev_start, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->h2d_stream, ev_start, 0);
+    if (e == cudaSuccess && k > 0) e = cudaMemcpyAsync(dB, B_host, (size_t)k * n * 8, cudaMemcpyHostToDevice, ctx->h2d_stream);
+    if (e == cudaSuccess) e = cudaEventRecord(ev_b, ctx->h2d_stream);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->stream, ev_b, 0);
+    const long long nchunks = (rows + chunk - 1) / chunk;
+    for (long long c = 0; c < nchunks && e == cudaSuccess && rc == MB_OK; ++c) {
+        const int s_ = (int)(c % SLOTS);
+        const long long r0 = c * chunk;
+        const int nr = (int)std::min<long long>(chunk, rows - r0);
+        if (c >= SLOTS) {                       // the slot's previous tenant: its GEMM has read A, its download has read C
+            e = cudaStreamWaitEvent(ctx->h2d_stream, ev_gemm[s_], 0);
+            if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->stream, ev_down[s_], 0);
+            if (e != cudaSuccess) break;
+        }
+        if (k > 0) e = cudaMemcpyAsync(dA(s_), A_host + (size_t)r0 * k, (size_t)nr * k * 8, cudaMemcpyHostToDevice, ctx->h2d_stream);
+        if (e == cudaSuccess) e = cudaEventRecord(ev_up[s_], ctx->h2d_stream);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->stream, ev_up[s_], 0);
+        if (e != cudaSuccess) break;
+        // row-major (nr x n) C chunk == column-major (n x nr) C^T = B^T (n x k) * A^T (k x nr, the row-major chunk itself)
+        rc = dgemm_device_impl(ctx, 'T', 'N', n, nr, k, 1.0, dB, kk, dA(s_), kk, 0.0, dC(s_), n, false);
+        if (rc != MB_OK) break;
+        e = cudaEventRecord(ev_gemm[s_], ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->d2h_stream, ev_gemm[s_], 0);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(C_host + (size_t)r0 * n, dC(s_), (size_t)nr * n * 8, cudaMemcpyDeviceToHost, ctx->d2h_stream);
+        if (e == cudaSuccess) e = cudaEventRecord(ev_down[s_], ctx->d2h_stream);
+    }
+    if (e == cudaSuccess && rc == MB_OK) {
+        // returns when every row is on the host; ctx->stream is ordered behind the downloads too
+        for (int s_ = 0; s_ < SLOTS && e == cudaSuccess; ++s_)
+            if (s_ < nchunks) e = cudaStreamWaitEvent(ctx->stream, ev_down[s_], 0);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->d2h_stream);
+    } else {
+        cudaStreamSynchronize(ctx->h2d_stream); cudaStreamSynchronize(ctx->stream); cudaStreamSynchronize(ctx->d2h_stream);
+    }
+    if (ev_start) cudaEventDestroy(ev_start);
+    if (ev_b) cudaEventDestroy(ev_b);
+    for (int s_ = 0; s_ < SLOTS; ++s_) {
+        if (ev_up[s_]) cudaEventDestroy(ev_up[s_]);
+        if (ev_gemm[s_]) cudaEventDestroy(ev_gemm[s_]);
+        if (ev_down[s_]) cudaEventDestroy(ev_down[s_]);
+    }
+    if (rc != MB_OK) return rc;
+    if (e != cudaSuccess) return cuda_fail(e, "mb_matmul_rowsharded_host");
     return MB_OK;
 }
 

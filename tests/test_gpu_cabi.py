@@ -389,6 +389,36 @@ def test_matmul_blocked_host_pipelined(gpu, oracle, dims):
                 assert np.abs(c_arr[i * n + j] - ref[(i, j)]).max() <= 1e-12
 
 
+@pytest.mark.parametrize("dims", [(1000, 1024, 96), (777, 130, 1030), (5, 3, 2), (300, 64, 1), (129, 0, 7)])
+def test_matmul_rowsharded_host_pipelined(gpu, oracle, dims, monkeypatch):
+    """mb_matmul_rowsharded_host: row-major rows in, row-major rows out (DenseVecMatrix.multiply(B: BDM) for JVM-held
+    rows), many chunks through the three-slot ring (the chunk size is forced down to 1 MiB), and the device-resident
+    twin mb_matmul_rowsharded on transposed views."""
+    lib, ctx = gpu
+    monkeypatch.setenv("MARLIN_B200_ROWSHARD_CHUNK_MIB", "1")
+    rows, k, n = dims
+    rng = np.random.default_rng(rows + k)
+    A = np.ascontiguousarray(rng.random((rows, k)) - 0.5)            # row-major rows
+    B = np.asfortranarray(rng.random((k, n)) - 0.5)
+    Cm = np.full((rows, n), np.nan)
+    ref = A @ B
+    denom = np.abs(A) @ np.abs(B)
+    denom[denom == 0] = 1.0
+    for _ in range(2):
+        nat.check(lib.mb_matmul_rowsharded_host(ctx, _vp(A), rows, k, _vp(B), n, _vp(Cm)))
+        assert (np.abs(Cm - ref) / denom).max() <= TOL
+    if k > 0:
+        ha = upload(gpu, A.reshape(-1), 0, rows, k, max(1, k), 1)
+        hb = upload_mat(gpu, B)
+        hct = alloc(gpu, n, rows)
+        vct = nat.c_blk()
+        nat.check(lib.mb_block_view_t(ctx, hct, C.byref(vct)))
+        nat.check(lib.mb_matmul_rowsharded(ctx, ha, hb, vct))
+        assert (np.abs(download(gpu, hct, n, rows).T - ref) / denom).max() <= TOL
+        if k != n:
+            assert lib.mb_matmul_rowsharded(ctx, hb, hb, vct) == nat.MB_ERR_DIM_MISMATCH
+
+
 def test_dgemm_degenerate_cases(gpu):
     """netlib dgemm corner cases: k = 0 and alpha = 0 reduce to C := beta*C (dgemm.f quick returns), m or n = 0 is a no-op,
     bad arguments are rejected like xerbla."""
