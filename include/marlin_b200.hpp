@@ -460,6 +460,19 @@ public:
         data_.multiplyInto(B, c, false);
         return DenseVecMatrix(ids_, c, 0, Bm.cols);
     }
+    // multiply(vector: BDV[Double]): BDV[Double] :171-184 — every row dotted with the broadcast vector: one gemv over the
+    // row-major shard, results placed by row id
+    std::vector<double> multiply(const std::vector<double>& vector) {
+        if (ids_.empty()) return {};
+        if (data_.cols() != (int)vector.size())
+            throw std::invalid_argument("Dimension mismatch during matrix-vector multiplication: " + std::to_string(data_.cols()) + " vs " + std::to_string(vector.size()));
+        DenseMatrix y = data_.multiply(SubMatrix(vector)).denseBlock();
+        std::vector<double> out(ids_.size(), 0.0);
+        for (size_t p = 0; p < ids_.size(); ++p) out.at((size_t)ids_[p]) = y.data[p];
+        return out;
+    }
+    inline DistributedVector multiply(const std::vector<double>& vector, int splitMode);            // :162-165
+    inline DistributedVector multiply(DistributedVector& vector, std::pair<int, int> splitMode);    // :149-154
     // multiply(other, splitMode) :109-141 — rows -> blocks (toBlocks) + the seq-keyed block products
     BlockMatrix multiply(DenseVecMatrix& other, std::tuple<int, int, int> splitMode) {
         if (numCols() != other.numRows()) throw std::invalid_argument("Dimension mismatch during matrix-matrix multiplication: " + std::to_string(numCols()) + " vs " + std::to_string(other.numRows()));
@@ -757,6 +770,17 @@ inline DistributedVector BlockMatrix::multiply(const std::vector<double>& v) {
     std::sort(sorted.begin(), sorted.end(), [](auto& a, auto& b) { return a.first < b.first; });
     for (auto& kv : sorted) res.emplace_back(kv.first.row, kv.second.multiply(x));
     return DistributedVector(res, numRows(), numBlksByRow());
+}
+
+inline DistributedVector DenseVecMatrix::multiply(const std::vector<double>& vector, int splitMode) {
+    BlockMatrix b = toBlockMatrix(splitMode, 1);
+    return b.multiply(vector);
+}
+inline DistributedVector DenseVecMatrix::multiply(DistributedVector& vector, std::pair<int, int> splitMode) {
+    if (numCols() != vector.length())
+        throw std::invalid_argument("Dimension mismatch during matrix-matrix multiplication: " + std::to_string(numCols()) + " vs " + std::to_string(vector.length()));
+    BlockMatrix b = toBlockMatrix(splitMode.first, splitMode.second);
+    return b.multiply(vector);
 }
 
 // ---------------------------------------------------------------------------------------------- MTUtils

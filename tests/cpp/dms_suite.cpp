@@ -221,6 +221,9 @@ int main() {
         BlockMatrix tall = mat.toBlockMatrix(2, 1);
         CHECK(tall.multiply(x).toBreeze() == y);
         CHECK(throws<std::invalid_argument>([&] { ma.multiply(x); }));
+        CHECK(mat.multiply(x) == y);                                              // DenseVecMatrix.scala:171-184
+        CHECK(mat.multiply(x, 2).toBreeze() == y);                                // :162-165
+        CHECK(mat.multiply(dv, std::make_pair(2, 2)).toBreeze() == y);            // :149-154
     });
     // beyond the reference suite: error behaviour and the generators
     test("dimension mismatch is an IllegalArgumentException", [&] {               // BlockMatrix.scala:150-151, DenseVecMatrix.scala:199-200
