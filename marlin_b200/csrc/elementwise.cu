@@ -373,7 +373,8 @@ constexpr int FILL_LVL0 = 9;        // thread offset = t * 2 * FILL_PER_THREAD s
 __global__ void __launch_bounds__(256) fill_uniform_kernel(double* out, long long rs, long long cs, int rows, int cols,
                                                           int row_major, unsigned long long state0, long long first,
                                                           double lo, double hi) {
-    __shared__ double stage[256][FILL_ROUND + 1];
+    __shared__ __align__(16) double stage[256][FILL_ROUND + 2];      // row stride 18 doubles: 16-byte aligned rows,
+                                                                     // conflict-free 128-bit accesses per quarter warp
     __shared__ unsigned long long jump_s[8][64];
     __shared__ unsigned long long base_s;
     const long long total = (long long)rows * cols;
@@ -411,40 +412,65 @@ __global__ void __launch_bounds__(256) fill_uniform_kernel(double* out, long lon
             s = t;
         }
     }
-    const long long i0 = block_first + (long long)threadIdx.x * FILL_PER_THREAD;
     const double span = __dsub_rn(hi, lo);
     // storage contiguous in fill order (a row-major shard filled row-major, or a packed column-major block filled
     // column-major): linear index == storage index, no 64-bit divisions on the store path
     const bool linear = row_major ? (cs == 1 && rs == cols) : (rs == 1 && cs == rows);
-    const long long block_end = min(total, block_first + 256ll * FILL_PER_THREAD);
+    const int block_cnt = (int)min((long long)256 * FILL_PER_THREAD, total - block_first);     // values this CTA owns
+    const int my_first = threadIdx.x * FILL_PER_THREAD;                                         // relative to block_first
+    double* dst = out + block_first;
+    const bool vec = linear && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
 #pragma unroll 1
     for (int round = 0; round < FILL_PER_THREAD / FILL_ROUND; ++round) {
-        if (block_first + (long long)round * FILL_ROUND >= block_end) break;      // uniform: nothing left for any thread
-        if (i0 + (long long)round * FILL_ROUND < total) {
+        if (round * FILL_ROUND >= block_cnt) break;       // uniform: thread 0's run is the earliest, nothing left for anyone
+        if (my_first + round * FILL_ROUND < block_cnt) {
 #pragma unroll
-            for (int v = 0; v < FILL_ROUND; ++v) {
-                s = xs_step(s);
-                const unsigned long long hi26 = s & ((1ull << 26) - 1);
-                s = xs_step(s);
-                const unsigned long long lo27 = s & ((1ull << 27) - 1);
-                const double u = (double)((hi26 << 27) + lo27) * 0x1.0p-53;
-                stage[threadIdx.x][v] = __dadd_rn(__dmul_rn(span, u), lo);
+            for (int v = 0; v < FILL_ROUND; v += 2) {
+                double2 pr;
+                {
+                    s = xs_step(s);
+                    const unsigned long long hi26 = s & ((1ull << 26) - 1);
+                    s = xs_step(s);
+                    const unsigned long long lo27 = s & ((1ull << 27) - 1);
+                    pr.x = __dadd_rn(__dmul_rn(span, (double)((hi26 << 27) + lo27) * 0x1.0p-53), lo);
+                }
+                {
+                    s = xs_step(s);
+                    const unsigned long long hi26 = s & ((1ull << 26) - 1);
+                    s = xs_step(s);
+                    const unsigned long long lo27 = s & ((1ull << 27) - 1);
+                    pr.y = __dadd_rn(__dmul_rn(span, (double)((hi26 << 27) + lo27) * 0x1.0p-53), lo);
+                }
+                *reinterpret_cast<double2*>(&stage[threadIdx.x][v]) = pr;
             }
         }
         __syncthreads();
-        // element e of the round: owner thread e / FILL_ROUND, its value j = e % FILL_ROUND -> 16 consecutive lanes
-        // write one 128-byte line
+        // pair p of the round: owner thread p / 8, its values 2*(p % 8), +1 -> 8 consecutive lanes write one 128-byte line
+        if (vec) {
+#pragma unroll
+            for (int p = threadIdx.x; p < 256 * (FILL_ROUND / 2); p += 256) {
+                const int owner = p >> 3, j = (p & 7) * 2;
+                const int idx = owner * FILL_PER_THREAD + round * FILL_ROUND + j;
+                if (idx + 1 < block_cnt) {
+                    *reinterpret_cast<double2*>(dst + idx) = *reinterpret_cast<const double2*>(&stage[owner][j]);
+                } else if (idx < block_cnt) {
+                    dst[idx] = stage[owner][j];
+                }
+            }
+        } else {
 #pragma unroll 4
-        for (int e = threadIdx.x; e < 256 * FILL_ROUND; e += 256) {
-            const int owner = e / FILL_ROUND, j = e % FILL_ROUND;
-            const long long i = block_first + (long long)owner * FILL_PER_THREAD + round * FILL_ROUND + j;
-            if (i < total) {
-                if (linear) {
-                    out[i] = stage[owner][j];
-                } else {
-                    long long r, c;
-                    if (row_major) { r = i / cols; c = i - r * cols; } else { c = i / rows; r = i - c * rows; }
-                    out[r * rs + c * cs] = stage[owner][j];
+            for (int e = threadIdx.x; e < 256 * FILL_ROUND; e += 256) {
+                const int owner = e / FILL_ROUND, j = e % FILL_ROUND;
+                const int idx = owner * FILL_PER_THREAD + round * FILL_ROUND + j;
+                if (idx < block_cnt) {
+                    if (linear) {
+                        dst[idx] = stage[owner][j];
+                    } else {
+                        const long long i = block_first + idx;
+                        long long r, c;
+                        if (row_major) { r = i / cols; c = i - r * cols; } else { c = i / rows; r = i - c * rows; }
+                        out[r * rs + c * cs] = stage[owner][j];
+                    }
                 }
             }
         }
