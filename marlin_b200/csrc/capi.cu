@@ -16,6 +16,7 @@
 #include <cstring>
 #include <new>
 #include <atomic>
+#include <mutex>
 #include <vector>
 
 struct mb_ctx {
@@ -40,6 +41,10 @@ struct mb_ctx {
     // partial vectors of the matrix x vector kernels (grow-only)
     double* vec_ws = nullptr;
     size_t vec_ws_doubles = 0;
+    // Entry points that use the context's own scratch buffers, workspaces, events or copy streams take this lock, so
+    // threads sharing one context (Spark local[N] task threads) serialise there; kernel-only entries (gemm, element-wise,
+    // transpose, fill) touch no shared host state and need none.  Threads that want concurrency use one context each.
+    std::recursive_mutex mu;
 };
 
 struct mb_block {
@@ -99,6 +104,7 @@ int32_t check_ctx(mb_ctx* ctx) {
         int32_t _r = check_ctx(ctx);       \
         if (_r != MB_OK) return _r;        \
     } while (0)
+#define MB_LOCK(ctx) std::lock_guard<std::recursive_mutex> _mb_lock((ctx)->mu)
 
 int32_t new_block(mb_block** out) {
     *out = new (std::nothrow) mb_block();
@@ -279,11 +285,13 @@ int64_t mb_launch_count(mb_ctx* ctx) { return ctx ? (int64_t)ctx->launches.load(
 
 int32_t mb_timer_start(mb_ctx* ctx) {
     MB_CTX(ctx);
+    MB_LOCK(ctx);
     MB_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
     return MB_OK;
 }
 int32_t mb_timer_stop(mb_ctx* ctx, float* ms_out) {
     MB_CTX(ctx);
+    MB_LOCK(ctx);
     if (!ms_out) return fail(MB_ERR_INVALID_ARG, "null ms_out");
     MB_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
     MB_CUDA(cudaEventSynchronize(ctx->ev1));
@@ -435,6 +443,7 @@ static int32_t dgemm_device_impl(mb_ctx* ctx, char transa, char transb, int32_t 
                                  const double* A, int32_t lda, const double* B, int32_t ldb, double beta, double* C,
                                  int32_t ldc, bool force_generic) {
     MB_CTX(ctx);
+    MB_LOCK(ctx);
     const bool ta = (transa == 'T' || transa == 't' || transa == 'C' || transa == 'c');
     const bool tb = (transb == 'T' || transb == 't' || transb == 'C' || transb == 'c');
     if (!ta && !(transa == 'N' || transa == 'n')) return fail(MB_ERR_INVALID_ARG, "dgemm: transa '%c'", transa);
@@ -665,6 +674,7 @@ int32_t mb_matmul_blocked_host(mb_ctx* ctx, const double* const* A_host, const d
                                int32_t k, int32_t n, const int32_t* row_len, const int32_t* k_len, const int32_t* col_len,
                                double* const* C_host) {
     MB_CTX(ctx);
+    MB_LOCK(ctx);
     if (!A_host || !B_host || !C_host || !row_len || !k_len || !col_len || m <= 0 || k <= 0 || n <= 0)
         return fail(MB_ERR_INVALID_ARG, "mb_matmul_blocked_host: bad argument");
     if (!ctx->h2d_stream) {
@@ -857,6 +867,7 @@ int32_t mb_matmul_rowsharded(mb_ctx* ctx, const mb_block* A_rows, const mb_block
 int32_t mb_matmul_rowsharded_host(mb_ctx* ctx, const double* A_host, int64_t rows, int32_t k, const double* B_host,
                                   int32_t n, double* C_host) {
     MB_CTX(ctx);
+    MB_LOCK(ctx);
     if (rows < 0 || k < 0 || n < 0 || (rows > 0 && ((k > 0 && !A_host) || (n > 0 && !C_host))) || (k > 0 && n > 0 && !B_host))
         return fail(MB_ERR_INVALID_ARG, "mb_matmul_rowsharded_host: bad argument");
     if (rows == 0 || n == 0) return MB_OK;
@@ -1032,6 +1043,7 @@ int32_t mb_block_transpose(mb_ctx* ctx, const mb_block* A, mb_block* out) {
 
 int32_t mb_block_sum(mb_ctx* ctx, const mb_block* A, double* sum_out) {
     MB_CTX(ctx);
+    MB_LOCK(ctx);
     if (!A || !sum_out) return fail(MB_ERR_INVALID_ARG, "mb_block_sum: null argument");
     if (A->dtype != MB_F64) return fail(MB_ERR_UNSUPPORTED, "mb_block_sum: fp64 blocks only");
     if (A->rows == 0 || A->cols == 0) { *sum_out = 0.0; return MB_OK; }
@@ -1046,6 +1058,7 @@ int32_t mb_block_sum(mb_ctx* ctx, const mb_block* A, double* sum_out) {
 
 int32_t mb_block_gemv(mb_ctx* ctx, const mb_block* A, const mb_block* x, mb_block* y, int32_t accumulate) {
     MB_CTX(ctx);
+    MB_LOCK(ctx);
     if (!A || !x || !y) return fail(MB_ERR_INVALID_ARG, "mb_block_gemv: null block");
     vec_view xv, yv;
     if (A->dtype != MB_F64 || !as_vector(x, &xv) || !as_vector(y, &yv))
@@ -1072,6 +1085,7 @@ int32_t mb_block_gemv(mb_ctx* ctx, const mb_block* A, const mb_block* x, mb_bloc
 
 int32_t mb_block_dot(mb_ctx* ctx, const mb_block* x, const mb_block* y, double* dot_out) {
     MB_CTX(ctx);
+    MB_LOCK(ctx);
     if (!x || !y || !dot_out) return fail(MB_ERR_INVALID_ARG, "mb_block_dot: null argument");
     vec_view xv, yv;
     if (!as_vector(x, &xv) || !as_vector(y, &yv))

@@ -438,3 +438,50 @@ def test_dgemm_degenerate_cases(gpu):
     assert lib.mb_dgemm_device(ctx, b"X", b"N", 4, 3, 2, 1.0, p(A), 4, p(A), 2, 0.0, p(Cm), 4) == nat.MB_ERR_INVALID_ARG
     assert lib.mb_dgemm_device(ctx, b"N", b"N", 4, 3, 2, 1.0, p(A), 3, p(A), 2, 0.0, p(Cm), 4) == nat.MB_ERR_INVALID_ARG   # lda < m
     assert lib.mb_dgemm_device(ctx, b"N", b"N", -1, 3, 2, 1.0, p(A), 4, p(A), 2, 0.0, p(Cm), 4) == nat.MB_ERR_INVALID_ARG
+
+
+def test_threads_share_blocks(gpu, oracle):
+    """Spark local[N] runs tasks as threads of one JVM (LocalSparkContext.scala:11): (i) threads with one context EACH
+    run concurrently on shared block handles; (ii) threads sharing ONE context serialise on its lock where the context's
+    scratch is used (sum, dot, gemv) and still get the right answers."""
+    import threading
+    lib, ctx = gpu
+    rng = np.random.default_rng(77)
+    A, B = rng.random((300, 200)) - 0.5, rng.random((200, 260)) - 0.5
+    x = rng.random(200)
+    ha, hb, hx = upload_mat(gpu, A), upload_mat(gpu, B), upload_mat(gpu, x.reshape(-1, 1))
+    ref_c, ref_y, ref_s = A @ B, A @ x, float(A.sum())
+    errors = []
+
+    def work(own_ctx):
+        try:
+            c = ctx
+            if own_ctx:
+                c = nat.c_ctx()
+                nat.check(lib.mb_init(0, C.byref(c)))
+            for _ in range(20):
+                hc, hy = nat.c_blk(), nat.c_blk()
+                nat.check(lib.mb_block_alloc(c, 300, 260, nat.MB_F64, C.byref(hc)))
+                nat.check(lib.mb_block_alloc(c, 300, 1, nat.MB_F64, C.byref(hy)))
+                nat.check(lib.mb_block_gemm(c, ha, hb, hc, 0))
+                nat.check(lib.mb_block_gemv(c, ha, hx, hy, 0))
+                s = C.c_double()
+                nat.check(lib.mb_block_sum(c, ha, C.byref(s)))
+                got_c = np.empty((300, 260), order="F"); got_y = np.empty((300, 1), order="F")
+                nat.check(lib.mb_block_download(c, hc, _vp(got_c), 300))
+                nat.check(lib.mb_block_download(c, hy, _vp(got_y), 300))
+                assert np.abs(got_c - ref_c).max() <= 1e-12 and np.abs(got_y[:, 0] - ref_y).max() <= 1e-12
+                assert abs(s.value - ref_s) <= 1e-10
+                lib.mb_block_free(c, hc); lib.mb_block_free(c, hy)
+            if own_ctx:
+                lib.mb_shutdown(c)
+        except Exception as exc:                      # surfaced in the main thread
+            errors.append(repr(exc))
+
+    for own in (True, False):
+        threads = [threading.Thread(target=work, args=(own,)) for _ in range(4)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        assert not errors, errors
