@@ -9,11 +9,9 @@ from ._common import millis, start, stop
 
 def main(args):
     if len(args) < 4:
-        print("usage: BLAS3 <matrixA row length> <matrixA column length> <matrixB column length> <mode> <m> <k> <n> ")
-        print("mode 1 means collect the two matrix to local, and then execute multiplication")
-        print("mode 2 means broadcast one of the matrix out, and then execute multiplication")
-        print("mode 3 means shuffle the two distributed matrix, and then execute multiplication")
-        print("for example: BLAS3 10000 10000 10000 1 5 5 5 ")
+        print("usage: blas3 <rows of A> <cols of A> <cols of B> <mode> [<m> [<k> <n>]]")
+        print("  mode 1: both operands as one block each on one GPU;  mode 2: row-sharded A times a replicated local B (m shards);")
+        print("  mode 3: both operands distributed, split (m, k, n).   e.g. blas3 10000 10000 10000 3 2 2 2")
         sys.exit(1)
     mb, rank = start()
     rowA, colA, colB, mode = int(args[0]), int(args[1]), int(args[2]), int(args[3])

@@ -7,8 +7,7 @@ from ._common import start, stop
 
 def main(args):
     if len(args) < 4:
-        sys.stderr.write("arguments wrong, the arguments should be <matrix A rows> <matrix A columns/ matrix B rows> "
-                         "<matrix B columns> <cores across the cluster>  + optional parameter{<broadcast threshold>}\n")
+        sys.stderr.write("usage: matrix_multiply <rows of A> <cols of A = rows of B> <cols of B> <cores> [<broadcast threshold, MB>]\n")
         sys.exit(-1)
     mb, rank = start()
     rowA, colA, colB = int(args[0]), int(args[1]), int(args[2])

@@ -7,10 +7,8 @@ from ._common import millis, start, stop
 
 def main(args):
     if len(args) < 7:
-        print("usage: RMMcompare <matrixA row length> <matrixA column length> <matrixB column length> <mode> <m> <k> <n>")
-        print("mode 2 means RMMv2")
-        print("for example: RMMcompare 30000 30000 30000 1 6 6 6")
-        print("*** NOTES, only support RMM-opt")
+        print("usage: rmm_compare <rows of A> <cols of A> <cols of B> <mode> <m> <k> <n>   (mode 2 = BlockMatrix x BlockMatrix,")
+        print("  the only mode the reference's RMMcompare still runs), e.g. rmm_compare 30000 30000 30000 2 6 6 6")
         sys.exit(1)
     mb, rank = start()
     rowA, colA, colB, mode = int(args[0]), int(args[1]), int(args[2]), int(args[3])

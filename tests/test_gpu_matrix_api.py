@@ -255,8 +255,8 @@ def test_multiply_by_local_matrix(M):
 
 def test_example_drivers(M, capsys):
     """The reference's multiply drivers (examples/MatrixMultiply, BLAS3, RMMcompare) with their own command lines."""
-    from marlin_b200.examples import BLAS3, MatrixMultiply, RMMcompare
-    MatrixMultiply.main(["300", "200", "100", "8"])
+    from marlin_b200.examples import blas3 as BLAS3, matrix_multiply, rmm_compare as RMMcompare
+    matrix_multiply.main(["300", "200", "100", "8"])
     BLAS3.main(["256", "128", "64", "2", "2"])
     BLAS3.main(["256", "128", "64", "3", "2", "2", "2"])
     RMMcompare.main(["256", "256", "256", "2", "2", "2", "2"])
