@@ -25,10 +25,12 @@ def elem_owner(row: int, col: int, blks_by_col: int, world: int) -> int:
 
 
 def product_rank(seq: int, num_products: int, world: int) -> int:
-    """Rank that runs block product `seq`.  Products are dealt out in contiguous seq ranges so that
-    the kk-partials of one C tile (consecutive seq) stay on one rank whenever m*n >= G (C-stationary,
-    no reduction traffic); with fewer C tiles than ranks the k dimension is split across ranks.
-    With G = m*k*n this is the reference's identity map partition -> executor."""
+    """Rank that runs block product `seq`.  Products are dealt out evenly in contiguous seq ranges, so the
+    kk-partials of one C tile (consecutive seq) stay on one rank whenever the ranks get whole C tiles
+    (m*n a multiple of G: C-stationary, no reduction traffic); otherwise a kk-group may straddle two ranks
+    and that C tile is reduced onto the rank of its kk = 0 partial — an even load beats an idle GPU.
+    With fewer C tiles than ranks the k dimension is split across ranks; with G = m*k*n this is the
+    reference's identity map partition -> executor."""
     if num_products >= world:
         return (seq * world) // num_products
     return seq
