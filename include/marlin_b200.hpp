@@ -144,7 +144,8 @@ public:
     // vectors are single-column blocks: BDM * BDV goes through multiply() above (dgemv), v.t * w and v * w.t here
     explicit SubMatrix(const std::vector<double>& v) {                                // new DenseVector(array)
         mb_block* b = nullptr;
-        check(mb_block_upload(Context::get(), v.data(), 0, (int)v.size(), 1, std::max<int>(1, (int)v.size()), 0, MB_F64, &b));
+        if (v.empty()) check(mb_block_alloc(Context::get(), 0, 1, MB_F64, &b));       // an empty piece (more splits than elements)
+        else check(mb_block_upload(Context::get(), v.data(), 0, (int)v.size(), 1, (int)v.size(), 0, MB_F64, &b));
         own(b);
     }
     double dot(const SubMatrix& o) const { double d = 0; check(mb_block_dot(Context::get(), h_.get(), o.h_.get(), &d)); return d; }      // DistributedVector.scala:167
