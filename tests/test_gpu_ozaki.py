@@ -97,3 +97,23 @@ def test_native_mode_is_default_and_small_blocks_stay_native(gpu):
     native = run(gpu, A, B, 0)
     split_requested = run(gpu, A, B, 7)          # below the 256 threshold -> DMMA kernel, bit-identical
     assert np.array_equal(native, split_requested)
+
+
+@pytest.mark.xfail(strict=False, reason="written after the round's GPU budget was spent: the model has not met the hardware "
+                                        "yet; an XPASS means the kernel is bit-identical to the exact-integer model")
+@pytest.mark.parametrize("cfg", [(6, 1), (7, 1), (5, 2)])
+def test_int8_split_equals_exact_integer_model_bit_for_bit(gpu, cfg):
+    """Every step of the split is exact integer arithmetic (digit GEMMs accumulate in int32) and the groups are folded
+    into C in a fixed order with one fp64 rounding each, so the kernel's result is fully determined:
+    oracle/ozaki_model.py computes the same thing with numpy int64 and must agree to the last bit."""
+    from oracle import ozaki_model as om
+    slices, mode = cfg
+    rng = np.random.default_rng(slices)
+    A = (rng.random((300, 520)) - 0.3) * np.exp2(rng.integers(-6, 6, size=(300, 1)))
+    B = (rng.random((520, 700)) - 0.3) * np.exp2(rng.integers(-6, 6, size=(1, 700)))
+    want, _ = om.gemm(A, B, slices, 7 if mode == 1 else 8)
+    got = run(gpu, A, B, slices, mode=mode)
+    assert np.array_equal(got, want)
+    C0 = rng.standard_normal((300, 700))
+    want2, _ = om.gemm(A, B, slices, 7 if mode == 1 else 8, C0=C0)
+    assert np.array_equal(run(gpu, A, B, slices, C0=C0, mode=mode), want2)
