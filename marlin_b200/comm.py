@@ -12,7 +12,7 @@ given (NCCL for CUDA tensors, gloo for the CPU tests); it contains no arithmetic
 from __future__ import annotations
 
 from dataclasses import dataclass, field
-from typing import Callable, Dict, List, Optional, Sequence, Tuple
+from typing import Callable, Dict, List, Sequence, Tuple
 
 import torch
 

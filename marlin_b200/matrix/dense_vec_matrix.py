@@ -9,7 +9,7 @@ before its dgemm (`rowsMat(::, i) := row_i`, DenseVecMatrix.scala:1670-1675).
 from __future__ import annotations
 
 import math
-from typing import Dict, Iterable, List, Optional, Sequence, Tuple
+from typing import Dict, List, Optional, Tuple
 
 import numpy as np
 import torch
