@@ -90,6 +90,21 @@ def cpu_port_sample(size: int, grid: int, target_seconds: float, steps: int = 1,
     return flops / sec / 1e12, cores, sample, sec * 1e3
 
 
+def f2j_sample(n: int = 768):
+    """netlib-java's default backend is F2J, pure Java (the reference's README.md:31 says that is what runs unless
+    native BLAS is installed): the oracle's C restatement of that loop nest, one thread, no FMA, as its stand-in."""
+    import numpy as np
+    from oracle import reference_model as rm
+    rng = np.random.default_rng(7)
+    a, b = np.asfortranarray(rng.random((n, n))), np.asfortranarray(rng.random((n, n)))
+    rm.block_multiply(a[:64, :64], b[:64, :64], "f2j")
+    t0 = time.perf_counter()
+    rm.block_multiply(a, b, "f2j")
+    sec = time.perf_counter() - t0
+    return {"value": 2.0 * n ** 3 / sec / 1e12, "unit": "TFLOP/s", "cores": 1,
+            "sample": f"{n}^3 product through the reference-BLAS dgemm loop nest in C (-ffp-contract=off), the stand-in for F2J"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -101,7 +116,7 @@ def run_reference(args):
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"{args.size}x{args.size} fp64 BlockMatrix multiply, {args.grid}x{args.grid} grid (bounded sample per step)"},
-        "cpu_baseline": {"value": tf, "unit": "TFLOP/s", "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": tf, "unit": "TFLOP/s", "cores": cores, "kind": "port", "sample": sample, "f2j_single_thread": f2j_sample()},
         "e2e": {"value": tf, "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "reference = CPU restatement (oracle port, OpenBLAS dgemm standing in for Breeze->netlib-java); the Scala/Spark "
                 "reference itself cannot run here (no JVM)",
@@ -400,7 +415,8 @@ def run_ours(args):
     cpu_baseline = None
     if rank == 0 and ws == 1 and not args.no_cpu_baseline:
         tf, cores, sample, _ = cpu_port_sample(N, g, args.cpu_seconds)
-        cpu_baseline = {"value": tf, "unit": "TFLOP/s", "cores": cores, "kind": "port", "sample": sample}
+        cpu_baseline = {"value": tf, "unit": "TFLOP/s", "cores": cores, "kind": "port", "sample": sample,
+                        "f2j_single_thread": f2j_sample()}
 
     if rank == 0:
         par = {1: "1 GPU: all 8 block products local, k-sum accumulated in the GEMM epilogue",
