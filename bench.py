@@ -30,6 +30,7 @@ sys.path.insert(0, str(ROOT))
 
 FP64_PEAK_TFLOPS_MEASURED = 37.1   # scripts/dmma_bench.cu on this pool's B200 (profiles/r01_probe_*): 148 SM x 64 DFMA/clk x 1.965 GHz
 METRIC = "fp64 dense multiply throughput (2*N^3 flop), 16384x16384 BlockMatrix 2x2 grid"
+METRIC_TALL = "fp64 tall-skinny multiply throughput (2*M*K*N flop), DenseVecMatrix 1048576x1024 x 1024x1024"
 
 
 def parse():
@@ -53,10 +54,11 @@ def parse():
 
 
 # ------------------------------------------------------------------------------------------ CPU arm
-def cpu_port_sample(size: int, grid: int, target_seconds: float, steps: int = 1, warmup: int = 0):
+def cpu_port_sample(size: int, grid: int, target_seconds: float, steps: int = 1, warmup: int = 0, tall: bool = False):
     """The reference algorithm on host cores (oracle port, numpy/OpenBLAS dgemm on all threads), on a BOUNDED
     sample of the workload: one of the (grid^3) block products A(0,0) * B(0,0)[:, :w], w chosen so a step takes
-    about `target_seconds`.  Returns (tflops, cores, sample description, ms per step)."""
+    about `target_seconds` — or, for the tall-skinny workload, a slice of the rows of one partition times the broadcast
+    1024 x 1024 matrix (DenseVecMatrix.scala:1660-1680).  Returns (tflops, cores, sample description, ms per step)."""
     import numpy as np
     from oracle import reference_model as rm
     cores = os.cpu_count() or 1
@@ -70,6 +72,23 @@ def cpu_port_sample(size: int, grid: int, target_seconds: float, steps: int = 1,
     t0 = time.perf_counter()
     rm.block_multiply(a, b, "blas")
     gf = 2.0 * probe ** 3 / (time.perf_counter() - t0) / 1e9
+    if tall:
+        kdim = 1024
+        rows = int(target_seconds * gf * 1e9 / (2.0 * kdim * kdim))
+        rows = max(4096, min(65536, (rows // 1024) * 1024))
+        A = np.ascontiguousarray(rng.random((rows, kdim)))             # the partition's rows, row-major
+        B = np.asfortranarray(rng.random((kdim, kdim)))
+        times = []
+        for it in range(warmup + steps):
+            t0 = time.perf_counter()
+            rm.block_multiply(A, B, "blas")                            # rowsMat * B per partition
+            dt = time.perf_counter() - t0
+            if it >= warmup:
+                times.append(dt)
+        sec = statistics.median(times)
+        sample = (f"{rows} of the 1048576 rows (x{1048576 // rows} by flops) times the 1024x1024 broadcast matrix, numpy/OpenBLAS dgemm, "
+                  f"{cores} threads; median of {len(times)}")
+        return 2.0 * rows * kdim * kdim / sec / 1e12, cores, sample, sec * 1e3
     w = int(target_seconds * gf * 1e9 / (2.0 * bs * bs))
     w = max(64, min(bs, (w // 64) * 64))
     A = np.asfortranarray(rng.random((bs, bs)))
@@ -109,13 +128,16 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    tall = args.workload == "tallskinny"
     tf, cores, sample, ms = cpu_port_sample(args.size, args.grid, args.cpu_seconds, steps=max(1, args.steps),
-                                            warmup=min(1, args.warmup))
+                                            warmup=min(1, args.warmup), tall=tall)
     line = {
-        "impl": "reference", "metric": METRIC, "value": tf, "unit": "TFLOP/s", "n_gpus": args.gpus, "steps": args.steps,
+        "impl": "reference", "metric": METRIC_TALL if tall else METRIC, "value": tf, "unit": "TFLOP/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{args.size}x{args.size} fp64 BlockMatrix multiply, {args.grid}x{args.grid} grid (bounded sample per step)"},
+        "config": {"workload": ("DenseVecMatrix 1048576x1024 (row-sharded) x replicated 1024x1024, fp64 [BASELINE.json configs[3]] "
+                                "(bounded sample per step)") if tall else
+                               f"{args.size}x{args.size} fp64 BlockMatrix multiply, {args.grid}x{args.grid} grid (bounded sample per step)"},
         "cpu_baseline": {"value": tf, "unit": "TFLOP/s", "cores": cores, "kind": "port", "sample": sample, "f2j_single_thread": f2j_sample()},
         "e2e": {"value": tf, "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "reference = CPU restatement (oracle port, OpenBLAS dgemm standing in for Breeze->netlib-java); the Scala/Spark "
@@ -414,7 +436,7 @@ def run_ours(args):
 
     cpu_baseline = None
     if rank == 0 and ws == 1 and not args.no_cpu_baseline:
-        tf, cores, sample, _ = cpu_port_sample(N, g, args.cpu_seconds)
+        tf, cores, sample, _ = cpu_port_sample(N, g, args.cpu_seconds, tall=tall)
         cpu_baseline = {"value": tf, "unit": "TFLOP/s", "cores": cores, "kind": "port", "sample": sample,
                         "f2j_single_thread": f2j_sample()}
 
@@ -426,7 +448,7 @@ def run_ours(args):
         workload = (f"{N}x{N} fp64 BlockMatrix multiply, {g}x{g} block grid, (m,k,n)=({g},{g},{g}) "
                     f"[BASELINE.json configs[2]; also the 1-GPU target size]")
         if tall:
-            metric = "fp64 tall-skinny multiply throughput (2*M*K*N flop), DenseVecMatrix 1048576x1024 x 1024x1024"
+            metric = METRIC_TALL
             workload = "DenseVecMatrix 1048576x1024 (row-sharded) x replicated 1024x1024, fp64 [BASELINE.json configs[3]]"
         elif bf16:
             metric = f"bf16 dense multiply throughput (2*N^3 flop), {N}x{N} BlockMatrix {g}x{g} grid"

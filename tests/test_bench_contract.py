@@ -49,3 +49,9 @@ def test_our_arm_fails_loudly_without_gpu():
     out = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--steps", "1", "--warmup", "1"], stdout=subprocess.PIPE,
                          stderr=subprocess.PIPE, text=True, timeout=300)
     assert out.returncode != 0 and not [l for l in out.stdout.splitlines() if l.startswith("{")]
+
+
+def test_reference_arm_tallskinny_workload():
+    d = _run(["--impl", "reference", "--workload", "tallskinny", "--steps", "1", "--warmup", "1", "--cpu-seconds", "1"])
+    assert "tall-skinny" in d["metric"] and "configs[3]" in d["config"]["workload"]
+    assert d["value"] > 0 and "rows" in d["cpu_baseline"]["sample"] and d["cpu_baseline"]["f2j_single_thread"]["cores"] == 1
