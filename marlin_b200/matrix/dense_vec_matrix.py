@@ -395,8 +395,7 @@ class DenseVecMatrix(DistributedMatrix):
         return DenseVecMatrix(ids=ids, data=shard, nRows=nr, nCols=nc)
 
     # ------------------------------------------------------------------ I/O (next-row (f)-3)
-    def saveToFileSystem(self, path: str) -> None:
-        """:1042-1046 — `index:v,v,...` per row."""
+    def _save_rows(self, path: str) -> None:
         import os
         from ..utils.mt_utils import _jdouble
         rank, ws = world()
@@ -404,7 +403,22 @@ class DenseVecMatrix(DistributedMatrix):
         arr = self.data.toBreeze() if self.data is not None and len(self.ids) else np.zeros((0, 0))
         with open(os.path.join(path, f"part-{rank:05d}"), "w") as fh:
             for pos, idx in enumerate(self.ids):
-                fh.write(f"{int(idx)}:" + ",".join(_jdouble(v) for v in arr[pos, :]) + "\n")
+                fh.write(f"{int(idx)}:DenseVector(" + ", ".join(_jdouble(v) for v in arr[pos, :]) + ")\n")
+
+    def saveToFileSystem(self, path: str) -> None:
+        """:1042-1046 — one line per row, `t._1 + ":" + t._2.toString`.  The row is a Breeze DenseVector, whose toString
+        is `DenseVector(v0, v1, ...)`, so that is what the reference's files contain (its own loadMatrixFile cannot read
+        them back; MTUtils.loadMatrixFile here accepts both this and the plain `index:v,v,...` form)."""
+        self._save_rows(path)
+
+    def saveWithDescription(self, path: str) -> None:
+        """:1055-1064 — the rows as above plus `_description`: `MatrixName<TAB>N/A` / `MatrixSize<TAB>rows cols`."""
+        import os
+        self._save_rows(path)
+        rows, cols = self.numRows(), self.numCols()
+        if world()[0] == 0:
+            with open(os.path.join(path, "_description"), "w") as fh:
+                fh.write(f"MatrixName\tN/A\nMatrixSize\t{rows} {cols}")
 
     def print(self) -> None:
         arr = self.data.toBreeze() if self.data is not None else np.zeros((0, 0))

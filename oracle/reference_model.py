@@ -720,8 +720,13 @@ class DenseVecMatrix:
         return self.to_block_matrix(min(num_blocks, self.num_rows() // 2), 1).transpose()
 
     def save_lines(self) -> List[str]:
-        """saveToFileSystem :1042-1046: `index:v,v,...`"""
-        return [f"{i}:" + ",".join(_jdouble(x) for x in v) for i, v in self.rows]
+        """saveToFileSystem :1042-1046: `t._1 + ":" + t._2.toString`, and Breeze's DenseVector.toString is
+        `DenseVector(v0, v1, ...)` (valuesIterator.mkString("DenseVector(", ", ", ")"))."""
+        return [f"{i}:DenseVector(" + ", ".join(_jdouble(x) for x in v) + ")" for i, v in self.rows]
+
+    def description(self) -> str:
+        """saveWithDescription :1055-1064, content of `_description`."""
+        return f"MatrixName\tN/A\nMatrixSize\t{self.num_rows()} {self.num_cols()}"
 
 
 class DistributedVector:
@@ -830,14 +835,31 @@ def _squareish(m: int, k: int, n: int) -> bool:
 
 
 def _jdouble(v: float) -> str:
-    """java.lang.Double.toString for the values the tests use (shortest repr, always with a decimal point)."""
-    s = repr(float(v))
-    if "e" in s or "E" in s:
-        mant, exp = s.lower().split("e")
-        if "." not in mant:
-            mant += ".0"
-        return f"{mant}E{int(exp)}"
-    return s
+    """java.lang.Double.toString: shortest digits that round-trip, plain decimal for 1e-3 <= |v| < 1e7 and computerized
+    scientific notation (d.dddE[-]n) outside that range, always at least one digit after the point.  (JDKs before 19
+    print a few values with one digit more than the shortest, JDK-4511638; the shortest form is used here.)"""
+    v = float(v)
+    if v != v:
+        return "NaN"
+    if v in (float("inf"), float("-inf")):
+        return "Infinity" if v > 0 else "-Infinity"
+    if v == 0.0:
+        return "-0.0" if math.copysign(1.0, v) < 0 else "0.0"
+    from decimal import Decimal
+    sign, digs, exp = Decimal(repr(abs(v))).as_tuple()
+    digits = "".join(str(d) for d in digs).lstrip("0")
+    exp += len(digits) - len(digits.rstrip("0"))
+    digits = digits.rstrip("0") or "0"
+    lead = len(digits) + exp - 1                        # decimal exponent of the leading digit
+    neg = "-" if v < 0 else ""
+    if 1e-3 <= abs(v) < 1e7:
+        if lead >= 0:
+            whole = digits[:lead + 1].ljust(lead + 1, "0")
+            frac = digits[lead + 1:] or "0"
+        else:
+            whole, frac = "0", "0" * (-lead - 1) + digits
+        return f"{neg}{whole}.{frac}"
+    return f"{neg}{digits[0]}.{digits[1:] or '0'}E{lead}"
 
 
 # --------------------------------------------------------------------------------------------

@@ -275,3 +275,25 @@ def test_reference_tool_output_loads(oracle, golden_dir, tmp_path):
         got = mb.MTUtils.loadMatrixFile(None, str(p))            # host-resident rows: no arithmetic involved
         assert (got.numRows(), got.numCols()) == want.shape
         assert np.array_equal(got.toBreeze(), want)
+
+
+def test_dense_vec_matrix_save_formats(oracle, tmp_path):
+    """DenseVecMatrix.saveToFileSystem / saveWithDescription (matrix/DenseVecMatrix.scala:1042-1064) through the product's
+    host layer on host-resident rows (no arithmetic): the row text is Breeze's DenseVector.toString, the description
+    file has the two tab-separated lines, and the loader here reads the files back."""
+    import marlin_b200 as mb
+    rows = [(i, np.array(v)) for i, v in mc.DATA_ROWS]
+    mat, omat = mb.DenseVecMatrix(rows), oracle.DenseVecMatrix(rows)
+    mat.saveWithDescription(str(tmp_path / "out"))
+    lines = (tmp_path / "out" / "part-00000").read_text().splitlines()
+    assert lines == omat.save_lines()
+    assert lines[0] == "0:DenseVector(0.0, 1.0, 2.0, 3.0)" and lines[1].startswith("2:DenseVector(3.0, ")
+    assert (tmp_path / "out" / "_description").read_text() == "MatrixName\tN/A\nMatrixSize\t4 4" == omat.description()
+    (tmp_path / "out" / "_description").unlink()
+    again = mb.MTUtils.loadMatrixFile(None, str(tmp_path / "out"))
+    assert np.array_equal(again.toBreeze(), mc.EXPECTED_DENSE)
+    mat.saveToFileSystem(str(tmp_path / "plain"))
+    assert (tmp_path / "plain" / "part-00000").read_text().splitlines() == lines
+    big = mb.DenseVecMatrix([(0, np.array([1e-7, 123456789.125, -0.5, 1e21]))])
+    big.saveToFileSystem(str(tmp_path / "sci"))
+    assert (tmp_path / "sci" / "part-00000").read_text() == "0:DenseVector(1.0E-7, 1.23456789125E8, -0.5, 1.0E21)\n"
