@@ -28,6 +28,13 @@ from pathlib import Path
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
+# The CPU legs (cpu_baseline, --impl reference) time numpy/OpenBLAS dgemm on ALL host cores.  torch.distributed.run
+# exports OMP_NUM_THREADS=1 when nproc > 1 and OpenBLAS reads its thread count when the library is loaded, so the
+# request has to be in the environment BEFORE the first `import numpy` (this file imports numpy lazily, below this
+# line); cpu_threads() re-applies it through threadpoolctl and reports the count OpenBLAS really uses.
+HOST_CORES = os.cpu_count() or 1
+os.environ["OPENBLAS_NUM_THREADS"] = str(HOST_CORES)
+
 FP64_PEAK_TFLOPS_MEASURED = 37.1   # scripts/dmma_bench.cu on this pool's B200 (profiles/r01_probe_*): 148 SM x 64 DFMA/clk x 1.965 GHz
 METRIC = "fp64 dense multiply throughput (2*N^3 flop), 16384x16384 BlockMatrix 2x2 grid"
 METRIC_TALL = "fp64 tall-skinny multiply throughput (2*M*K*N flop), DenseVecMatrix 1048576x1024 x 1024x1024"
@@ -49,29 +56,52 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-int8-split", action="store_true")
-    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--cpu-seconds", type=float, default=3.0, help="target seconds per CPU sample step of the cpu_baseline leg")
+    ap.add_argument("--ref-seconds", type=float, default=3.0, help="target seconds per step of --impl reference")
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--no-extra-configs", action="store_true")
     return ap.parse_args()
 
 
 # ------------------------------------------------------------------------------------------ CPU arm
-def cpu_port_sample(size: int, grid: int, target_seconds: float, steps: int = 1, warmup: int = 0, tall: bool = False):
+def cpu_threads():
+    """Ask the BLAS behind numpy for every host core and return (threads it will really use, library description).
+    OpenBLAS wheels are built with a compile-time thread cap (64 or 128), so the count can be below os.cpu_count()."""
+    import numpy as np  # noqa: F401  (loads the BLAS)
+    try:
+        from threadpoolctl import threadpool_info, threadpool_limits
+        threadpool_limits(limits=HOST_CORES, user_api="blas")
+        infos = [i for i in threadpool_info() if i.get("user_api") == "blas"]
+        if infos:
+            i = infos[0]
+            return int(i.get("num_threads", 1)), f"{i.get('internal_api', 'blas')} {i.get('version', '')} ({i.get('threading_layer', 'pthreads')})"
+    except Exception:
+        pass
+    return int(os.environ.get("OPENBLAS_NUM_THREADS", "1")), "blas (threadpoolctl unavailable: thread count is the requested one)"
+
+
+def cpu_port_sample(size: int, grid: int, target_seconds: float, steps: int = 5, warmup: int = 1, tall: bool = False):
     """The reference algorithm on host cores (oracle port, numpy/OpenBLAS dgemm on all threads), on a BOUNDED
     sample of the workload: one of the (grid^3) block products A(0,0) * B(0,0)[:, :w], w chosen so a step takes
     about `target_seconds` — or, for the tall-skinny workload, a slice of the rows of one partition times the broadcast
-    1024 x 1024 matrix (DenseVecMatrix.scala:1660-1680).  Returns (tflops, cores, sample description, ms per step)."""
+    1024 x 1024 matrix (DenseVecMatrix.scala:1660-1680).  Median of >= 5 timed steps after a warm-up.
+    Returns a dict: value (TFLOP/s), threads (actually used), cores (host), sample, ms, extrapolation."""
     import numpy as np
     from oracle import reference_model as rm
-    cores = os.cpu_count() or 1
-    os.environ.setdefault("OPENBLAS_NUM_THREADS", str(cores))
+    threads, blas = cpu_threads()
+    steps = max(5, steps)
     bs = size // grid
     rng = np.random.default_rng(42)
-    probe = 1024
+    probe = 2048
     a = np.asfortranarray(rng.random((probe, probe)))
     b = np.asfortranarray(rng.random((probe, probe)))
     rm.block_multiply(a, b, "blas")
-    t0 = time.perf_counter()
-    rm.block_multiply(a, b, "blas")
-    gf = 2.0 * probe ** 3 / (time.perf_counter() - t0) / 1e9
+    best = 1e9
+    for _ in range(3):
+        t0 = time.perf_counter()
+        rm.block_multiply(a, b, "blas")
+        best = min(best, time.perf_counter() - t0)
+    gf = 2.0 * probe ** 3 / best / 1e9
     if tall:
         kdim = 1024
         rows = int(target_seconds * gf * 1e9 / (2.0 * kdim * kdim))
@@ -86,9 +116,11 @@ def cpu_port_sample(size: int, grid: int, target_seconds: float, steps: int = 1,
             if it >= warmup:
                 times.append(dt)
         sec = statistics.median(times)
-        sample = (f"{rows} of the 1048576 rows (x{1048576 // rows} by flops) times the 1024x1024 broadcast matrix, numpy/OpenBLAS dgemm, "
-                  f"{cores} threads; median of {len(times)}")
-        return 2.0 * rows * kdim * kdim / sec / 1e12, cores, sample, sec * 1e3
+        sample = (f"{rows} of the 1048576 rows times the 1024x1024 broadcast matrix, numpy/OpenBLAS dgemm on {threads} threads "
+                  f"({HOST_CORES} host cores); median of {len(times)} after {warmup} warm-up")
+        return {"value": 2.0 * rows * kdim * kdim / sec / 1e12, "threads": threads, "cores": HOST_CORES, "blas": blas, "sample": sample,
+                "ms": sec * 1e3, "extrapolation": {"by": "flops", "sample_flops": 2.0 * rows * kdim * kdim,
+                                                   "workload_flops": 2.0 * 1048576 * kdim * kdim}}
     w = int(target_seconds * gf * 1e9 / (2.0 * bs * bs))
     w = max(64, min(bs, (w // 64) * 64))
     A = np.asfortranarray(rng.random((bs, bs)))
@@ -104,9 +136,10 @@ def cpu_port_sample(size: int, grid: int, target_seconds: float, steps: int = 1,
             times.append(dt)
     sec = statistics.median(times)
     flops = 2.0 * bs * bs * w
-    sample = (f"one block product A(0,0)[{bs}x{bs}] * B(0,0)[:, :{w}] + one partial add, numpy/OpenBLAS dgemm, "
-              f"{cores} threads; median of {len(times)}")
-    return flops / sec / 1e12, cores, sample, sec * 1e3
+    sample = (f"one block product A(0,0)[{bs}x{bs}] * B(0,0)[:, :{w}] + one partial add, numpy/OpenBLAS dgemm on {threads} threads "
+              f"({HOST_CORES} host cores); median of {len(times)} after {warmup} warm-up; rate extrapolated to the whole multiply by flops")
+    return {"value": flops / sec / 1e12, "threads": threads, "cores": HOST_CORES, "blas": blas, "sample": sample, "ms": sec * 1e3,
+            "extrapolation": {"by": "flops", "sample_flops": flops, "workload_flops": 2.0 * size ** 3}}
 
 
 def f2j_sample(n: int = 768):
@@ -124,24 +157,63 @@ def f2j_sample(n: int = 768):
             "sample": f"{n}^3 product through the reference-BLAS dgemm loop nest in C (-ffp-contract=off), the stand-in for F2J"}
 
 
+def workload_config(args, ws: int) -> dict:
+    """The `config` object of the JSON line — the same for our arm and the reference arm at a given N."""
+    N, g = args.size, args.grid
+    tall, bf16 = args.workload == "tallskinny", args.dtype == "bf16"
+    par = {1: "1 GPU: all 8 block products local (one grouped launch), k-sum accumulated in registers",
+           2: "2 GPUs: 4 products each, k-sum local; tiles pulled over NVLink peer memory",
+           4: "4 GPUs: 2 products each (same C tile), k-sum local; tiles pulled over NVLink peer memory",
+           8: "8 GPUs: 1 product each (RDD partition == GPU); A/B tiles pulled over NVLink peer memory (copy engines), the k=2 "
+              "partials reduce-scattered between the two holders by the GEMM epilogue's peer stores"}
+    workload = (f"{N}x{N} fp64 BlockMatrix multiply, {g}x{g} block grid, (m,k,n)=({g},{g},{g}) "
+                f"[BASELINE.json configs[2]; also the 1-GPU target size]")
+    if tall:
+        workload = "DenseVecMatrix 1048576x1024 (row-sharded) x replicated 1024x1024, fp64 [BASELINE.json configs[3]]"
+    elif bf16:
+        workload = f"{N}x{N} bf16 BlockMatrix multiply, {g}x{g} block grid, fp32 accumulate / fp32 C tiles [BASELINE.json configs[4]]"
+    elif (N, g) != (16384, 2):
+        workload = f"{N}x{N} fp64 BlockMatrix multiply, {g}x{g} block grid"
+    headline = not (tall or bf16 or (N, g) != (16384, 2))
+    return {"workload": workload,
+            "parallelism": par.get(ws, f"{ws} GPUs") if headline else f"{ws} GPU(s), one process each",
+            "l2": "inputs (2 GiB per operand) are far larger than the 126 MB L2; no explicit flush",
+            "inputs": "U[0,1) fp64 from the on-device XORShift generator (MTUtils.randomBlockMatrix, seeds 42/43)"}
+
+
+def metric_name(args) -> str:
+    N, g = args.size, args.grid
+    if args.workload == "tallskinny":
+        return METRIC_TALL
+    if args.dtype == "bf16":
+        return f"bf16 dense multiply throughput (2*N^3 flop), {N}x{N} BlockMatrix {g}x{g} grid"
+    if (N, g) != (16384, 2):
+        return f"fp64 dense multiply throughput (2*N^3 flop), {N}x{N} BlockMatrix {g}x{g} grid"
+    return METRIC
+
+
 def run_reference(args):
+    """The reference's own CPU implementation of the path on the box's host cores.  The Scala/Spark/Breeze reference cannot
+    run here (no JVM), so this is the oracle port (kind "port"): the same block algorithm with numpy/OpenBLAS dgemm standing
+    in for Breeze -> netlib-java native BLAS, on every host core, one bounded sample of the workload per step.  Under
+    torchrun only rank 0 works; the thread count is forced and REPORTED (torchrun exports OMP_NUM_THREADS=1)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     tall = args.workload == "tallskinny"
-    tf, cores, sample, ms = cpu_port_sample(args.size, args.grid, args.cpu_seconds, steps=max(1, args.steps),
-                                            warmup=min(1, args.warmup), tall=tall)
+    r = cpu_port_sample(args.size, args.grid, args.ref_seconds, steps=max(5, args.steps), warmup=max(1, min(2, args.warmup)), tall=tall)
+    tf = r["value"]
     line = {
-        "impl": "reference", "metric": METRIC_TALL if tall else METRIC, "value": tf, "unit": "TFLOP/s", "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "impl": "reference", "metric": metric_name(args), "value": tf, "unit": "TFLOP/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": r["ms"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": ("DenseVecMatrix 1048576x1024 (row-sharded) x replicated 1024x1024, fp64 [BASELINE.json configs[3]] "
-                                "(bounded sample per step)") if tall else
-                               f"{args.size}x{args.size} fp64 BlockMatrix multiply, {args.grid}x{args.grid} grid (bounded sample per step)"},
-        "cpu_baseline": {"value": tf, "unit": "TFLOP/s", "cores": cores, "kind": "port", "sample": sample, "f2j_single_thread": f2j_sample()},
+        "config": workload_config(args, args.gpus),
+        "cpu_baseline": {"value": tf, "unit": "TFLOP/s", "cores": r["threads"], "host_cores": r["cores"], "kind": "port", "blas": r["blas"],
+                         "sample": r["sample"], "extrapolation": r["extrapolation"], "f2j_single_thread": f2j_sample()},
         "e2e": {"value": tf, "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "reference = CPU restatement (oracle port, OpenBLAS dgemm standing in for Breeze->netlib-java); the Scala/Spark "
-                "reference itself cannot run here (no JVM)",
+                "reference itself cannot run here (no JVM); each step times a bounded sample of the workload (cpu_baseline.sample) "
+                "and the rate is extrapolated by flops; ms_per_step is the sample's time, not the whole multiply's",
     }
     print(json.dumps(line), flush=True)
 
@@ -194,6 +266,73 @@ class ClockSampler:
         loaded = [s for s, p in zip(sm, pw) if p > 300] or sm
         return {"sm_mhz": statistics.median(loaded) if loaded else None, "sm_max_mhz": max(mx) if mx else None,
                 "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------ parity (checker, not product)
+def _tile(sub, torch):
+    """Logical (rows x cols) torch view of a packed column-major SubMatrix buffer, as fp64."""
+    t = sub.buf[: sub.rows * sub.cols].view(sub.cols, sub.rows).t()
+    return t if t.dtype == torch.float64 else t.to(torch.float64)
+
+
+def freivalds_blockmatrix(A, B, Cm, ws, tol, probes=3):
+    """Freivalds check of C = A*B on the device, at any number of ranks: for `probes` random vectors v (the same on every
+    rank), y = C v against z = A (B v), with every tile-times-vector product done by torch (cuBLAS dgemv — independent of
+    this repository's kernels) on the rank that holds the tile and the pieces summed with all_reduce.  Inputs are U[0,1),
+    so (|A||B||v|)_i = z_i and the scaled error is max_i |y - z|_i / z_i.  An error of relative size d in ONE element of
+    C moves its row sum by about d / n: with n = 16384 and tol = 1e-10 anything beyond ~2e-6 in a single element fails,
+    and a wrong / missing / misplaced tile fails by orders of magnitude."""
+    import torch
+    import torch.distributed as dist
+    dev = torch.device("cuda", torch.cuda.current_device())
+    M, K, N = A.numRows(), A.numCols(), B.numCols()
+    ceil = lambda a, b: -(-a // b)
+    bm, bk, bn = ceil(M, A.numBlksByRow()), ceil(K, A.numBlksByCol()), ceil(N, B.numBlksByCol())
+    gen = torch.Generator(device=dev).manual_seed(20260922)
+    worst = 0.0
+    for _ in range(probes):
+        v = torch.rand(N, generator=gen, device=dev, dtype=torch.float64)
+        w = torch.zeros(K, device=dev, dtype=torch.float64)
+        for b, s in B.blocks:
+            w[b.row * bk: b.row * bk + s.rows] += _tile(s, torch) @ v[b.column * bn: b.column * bn + s.cols]
+        if ws > 1:
+            dist.all_reduce(w)
+        z = torch.zeros(M, device=dev, dtype=torch.float64)
+        for b, s in A.blocks:
+            z[b.row * bm: b.row * bm + s.rows] += _tile(s, torch) @ w[b.column * bk: b.column * bk + s.cols]
+        y = torch.zeros(M, device=dev, dtype=torch.float64)
+        seen = torch.zeros(M, device=dev, dtype=torch.float64)
+        for b, s in Cm.blocks:
+            y[b.row * bm: b.row * bm + s.rows] += _tile(s, torch) @ v[b.column * bn: b.column * bn + s.cols]
+            seen[b.row * bm: b.row * bm + s.rows] += s.cols
+        if ws > 1:
+            dist.all_reduce(z); dist.all_reduce(y); dist.all_reduce(seen)
+        if not bool((seen == N).all()):
+            return {"max_scaled_err": float("inf"), "tol": tol, "ok": False, "method": "coverage: some C tile is missing or duplicated"}
+        worst = max(worst, float(((y - z).abs() / z).max().item()))
+    return {"max_scaled_err": worst, "tol": tol, "ok": bool(worst <= tol), "probes": probes, "n_ranks": ws,
+            "method": "Freivalds on device: C v vs A (B v), torch/cuBLAS dgemv per tile on its owner + all_reduce; max_i |y-z|_i / (|A||B||v|)_i"}
+
+
+def freivalds_rows(A_rows, B, C_rows, ws, tol, probes=3):
+    """The same for the row-sharded multiply C_rows = A_rows * B (every rank checks its own shard, worst over ranks)."""
+    import torch
+    import torch.distributed as dist
+    dev = torch.device("cuda", torch.cuda.current_device())
+    gen = torch.Generator(device=dev).manual_seed(20260922)
+    rowmajor = lambda s: s.buf[: s.rows * s.cols].view(s.rows, s.cols)
+    a, c, b = rowmajor(A_rows), rowmajor(C_rows), _tile(B, torch)
+    worst = 0.0
+    for _ in range(probes):
+        v = torch.rand(b.shape[1], generator=gen, device=dev, dtype=torch.float64)
+        z = a @ (b @ v)
+        worst = max(worst, float(((c @ v - z).abs() / z).max().item()))
+    t = torch.tensor([worst], device=dev, dtype=torch.float64)
+    if ws > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    worst = float(t.item())
+    return {"max_scaled_err": worst, "tol": tol, "ok": bool(worst <= tol), "probes": probes, "n_ranks": ws,
+            "method": "Freivalds on device per row shard: C v vs A (B v) with torch/cuBLAS dgemv; max_i |y-z|_i / (|A||B||v|)_i, worst rank"}
 
 
 # ------------------------------------------------------------------------------------------ GPU arm
@@ -254,9 +393,10 @@ def run_ours(args):
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
+    Cm = None
     for _ in range(args.steps):
-        Cm = step()
         del Cm
+        Cm = step()
     e1.record()
     barrier()
     ms_total = e0.elapsed_time(e1)
@@ -434,46 +574,46 @@ def run_ours(args):
             rt.set_fp64_mode("native")
             int8_split = {"error": str(exc)[:200]}
 
+    # ---- parity of the LAST timed result, on device, at every N (the checker is torch/cuBLAS dgemv, not this library) ----
+    parity = None
+    if not args.no_parity:
+        tol = 1e-4 if bf16 else 1e-10
+        if tall:
+            parity = freivalds_rows(A.data, B, Cm.data, ws, tol)
+        else:
+            parity = freivalds_blockmatrix(A, B, Cm, ws, tol)
+    del Cm
+
     cpu_baseline = None
-    if rank == 0 and ws == 1 and not args.no_cpu_baseline:
-        tf, cores, sample, _ = cpu_port_sample(N, g, args.cpu_seconds, tall=tall)
-        cpu_baseline = {"value": tf, "unit": "TFLOP/s", "cores": cores, "kind": "port", "sample": sample,
+    if rank == 0 and not args.no_cpu_baseline:
+        r = cpu_port_sample(N, g, args.cpu_seconds, tall=tall)
+        cpu_baseline = {"value": r["value"], "unit": "TFLOP/s", "cores": r["threads"], "host_cores": r["cores"], "kind": "port",
+                        "blas": r["blas"], "sample": r["sample"], "extrapolation": r["extrapolation"],
                         "f2j_single_thread": f2j_sample()}
+    if ws > 1:
+        dist.barrier()            # the other ranks wait for rank 0's CPU leg before tearing NCCL down
 
     if rank == 0:
-        par = {1: "1 GPU: all 8 block products local, k-sum accumulated in the GEMM epilogue",
-               2: "2 GPUs: 4 products each, k-sum local", 4: "4 GPUs: 2 products each (same C tile), k-sum local",
-               8: "8 GPUs: 1 product each (RDD partition == GPU), A/B tiles via grouped NCCL send/recv, pairwise reduce of partials"}
-        metric = METRIC
-        workload = (f"{N}x{N} fp64 BlockMatrix multiply, {g}x{g} block grid, (m,k,n)=({g},{g},{g}) "
-                    f"[BASELINE.json configs[2]; also the 1-GPU target size]")
-        if tall:
-            metric = METRIC_TALL
-            workload = "DenseVecMatrix 1048576x1024 (row-sharded) x replicated 1024x1024, fp64 [BASELINE.json configs[3]]"
-        elif bf16:
-            metric = f"bf16 dense multiply throughput (2*N^3 flop), {N}x{N} BlockMatrix {g}x{g} grid"
-            workload = f"{N}x{N} bf16 BlockMatrix multiply, {g}x{g} block grid, fp32 accumulate / fp32 C tiles [BASELINE.json configs[4]]"
-        elif (N, g) != (16384, 2):
-            metric = f"fp64 dense multiply throughput (2*N^3 flop), {N}x{N} BlockMatrix {g}x{g} grid"
-            workload = f"{N}x{N} fp64 BlockMatrix multiply, {g}x{g} block grid"
         line = {
-            "metric": metric, "value": value, "unit": "TFLOP/s", "n_gpus": ws, "steps": args.steps, "warmup": args.warmup,
+            "metric": metric_name(args), "value": value, "unit": "TFLOP/s", "n_gpus": ws, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "bf16" if bf16 else "f64",
             "data": "synthetic",
-            "config": {"workload": workload,
-                       "parallelism": par.get(ws, f"{ws} GPUs") if not (tall or bf16 or (N, g) != (16384, 2)) else f"{ws} GPU(s), one process each",
-                       "l2": "inputs (2 GiB per operand) are far larger than the 126 MB L2; no explicit flush",
-                       "inputs": "U[0,1) fp64 from the on-device XORShift generator (MTUtils.randomBlockMatrix, seeds 42/43)"},
-            "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu_baseline, "gpu_launches": int(launches),
+            "config": workload_config(args, ws),
+            "roofline": roofline, "e2e": e2e, "parity": parity, "cpu_baseline": cpu_baseline, "gpu_launches": int(launches),
             "fp64_on_int8_tensor_cores": int8_split,
             "clocks": clocks,
             "phases_ms_per_step": {k: v[0] / args.steps for k, v in phases.items()},
             "pct_of_tensor_peak": 100.0 * value / (peak * ws),
         }
+        if parity is not None and not parity["ok"]:
+            line["error"] = f"PARITY FAILED: scaled error {parity['max_scaled_err']:.3e} > {parity['tol']:.1e}; the timing above is of a wrong result"
+            line["value"] = None
         print(json.dumps(line), flush=True)
     if ws > 1:
         dist.destroy_process_group()
+    if parity is not None and not parity["ok"]:
+        raise SystemExit(3)
 
 
 def main():

@@ -606,7 +606,7 @@ int32_t mb_matmul_blocked_subset(mb_ctx* ctx, mb_block* const* A_tiles, mb_block
     std::vector<const double*> Ap(m * k, nullptr), Bp(k * n, nullptr);
     std::vector<double*> Cp(m * n, nullptr);
     std::vector<long long> lda(m * k, 2), ldb(k * n, 2), ldc(m * n, 2);
-    std::vector<int> row_len(m, 1), k_len(k, 1), col_len(n, 1);
+    std::vector<int> row_len(m, -1), k_len(k, -1), col_len(n, -1);    // -1 = not seen yet
     for (int c = 0; c < num_c && groupable; ++c) {
         const int id = c_ids[c], i = id / n, j = id % n;
         const mb_block* cb = C_tiles[id];
@@ -619,7 +619,9 @@ int32_t mb_matmul_blocked_subset(mb_ctx* ctx, mb_block* const* A_tiles, mb_block
             Ap[i * k + kk] = f64_ptr(a); lda[i * k + kk] = a->ld;
             Bp[kk * n + j] = f64_ptr(b); ldb[kk * n + j] = b->ld;
             // the k-slab count is shared by all C blocks: every A(.,kk) must have the same column count
-            if (k_len[kk] != 1 && k_len[kk] != a->cols) groupable = false;
+            if (k_len[kk] >= 0 && k_len[kk] != a->cols) groupable = false;
+            if (row_len[i] >= 0 && row_len[i] != a->rows) groupable = false;
+            if (col_len[j] >= 0 && col_len[j] != b->cols) groupable = false;
             k_len[kk] = a->cols;
             row_len[i] = a->rows; col_len[j] = b->cols;
         }

@@ -9,7 +9,9 @@
 #include "elementwise.h"
 #include "ptx.cuh"
 #include <cuda_bf16.h>
+#include <atomic>
 #include <cstdlib>
+#include <mutex>
 
 namespace mb {
 
@@ -639,10 +641,12 @@ static unsigned long long h_step(unsigned long long s) {
     return s;
 }
 cudaError_t fill_uniform_init_tables() {
-    static bool done[64] = {};
+    static std::mutex mu;                      // first calls from several host threads serialise here
+    static std::atomic<bool> done[64];
     int dev = 0;
     cudaGetDevice(&dev);
-    if (dev >= 0 && dev < 64 && done[dev]) return cudaSuccess;
+    if (dev >= 0 && dev < 64 && done[dev].load(std::memory_order_acquire)) return cudaSuccess;
+    std::lock_guard<std::mutex> lk(mu);
     static unsigned long long tab[40][64];
     static bool built = false;
     if (!built) {
@@ -659,7 +663,7 @@ cudaError_t fill_uniform_init_tables() {
         built = true;
     }
     cudaError_t e = cudaMemcpyToSymbol(g_jump, tab, sizeof(tab));
-    if (e == cudaSuccess && dev >= 0 && dev < 64) done[dev] = true;
+    if (e == cudaSuccess && dev >= 0 && dev < 64) done[dev].store(true, std::memory_order_release);
     return e;
 }
 

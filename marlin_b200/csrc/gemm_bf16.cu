@@ -18,6 +18,7 @@
 //   B 'T' (N x K, n contiguous)  -> MN-major B : 4 atoms [64 k-rows][64 n]
 #include "gemm_bf16.h"
 #include "ptx.cuh"
+#include <atomic>
 #include <cuda_bf16.h>
 
 namespace mb {
@@ -329,11 +330,11 @@ bool make_map_bf16(CUtensorMap* map, const void* base, uint64_t dim0, uint64_t d
 template <bool TA, bool TB>
 cudaError_t launch(const SegMaps& maps, const Params& p, int num_sms, cudaStream_t stream) {
     auto kern = gemm_bf16_tcgen05_kernel<TA, TB>;
-    static bool attr_done = false;
-    if (!attr_done) {
+    static std::atomic<bool> attr_done{false};   // idempotent attribute set; atomic so threads sharing a context may race here
+    if (!attr_done.load(std::memory_order_acquire)) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
         if (e != cudaSuccess) return e;
-        attr_done = true;
+        attr_done.store(true, std::memory_order_release);
     }
     const int grid = min(p.tiles_m * p.tiles_n, num_sms);
     kern<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(maps, p);

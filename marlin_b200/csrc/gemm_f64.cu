@@ -19,6 +19,7 @@
 // contiguous dimension is K ("K form") as one box of [128 mn-rows][16 k].
 #include "gemm_f64.h"
 #include "ptx.cuh"
+#include <atomic>
 
 namespace mb {
 
@@ -525,11 +526,12 @@ template <bool TA, bool TB>
 cudaError_t launch_dmma(const CUtensorMap& mA, const CUtensorMap& mB, const Params& p, int num_sms,
                         cudaStream_t stream) {
     auto kern = gemm_f64_dmma_kernel<TA, TB>;
-    static bool attr_done = false;   // per template instantiation
-    if (!attr_done) {
+    // per template instantiation; idempotent, so concurrent first calls may both set it (no unsynchronised flag)
+    static std::atomic<bool> attr_done{false};
+    if (!attr_done.load(std::memory_order_acquire)) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
         if (e != cudaSuccess) return e;
-        attr_done = true;
+        attr_done.store(true, std::memory_order_release);
     }
     const int grid = min(p.tiles_m * p.tiles_n, num_sms);
     kern<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(mA, mB, p);
@@ -638,11 +640,11 @@ cudaError_t gemm_f64_grouped(int m, int k, int n, const int* my_c, int num_c, co
         g.tiles_n[c] = (col_len[j] + BN - 1) / BN;
         g.tile_start[c + 1] = g.tile_start[c] + g.tiles_m[c] * g.tiles_n[c];
     }
-    static bool attr_done = false;
-    if (!attr_done) {
+    static std::atomic<bool> attr_done{false};
+    if (!attr_done.load(std::memory_order_acquire)) {
         cudaError_t e = cudaFuncSetAttribute(gemm_f64_dmma_grouped_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
         if (e != cudaSuccess) return e;
-        attr_done = true;
+        attr_done.store(true, std::memory_order_release);
     }
     const int grid = min(g.tile_start[num_c], num_sms);
     gemm_f64_dmma_grouped_kernel<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(g);

@@ -17,6 +17,7 @@
 // and an fp64 read-modify-write epilogue.
 #include "gemm_ozaki.h"
 #include "ptx.cuh"
+#include <atomic>
 #include <cstdlib>
 
 namespace mb {
@@ -657,22 +658,22 @@ cudaError_t gemm_f64_ozaki(int M, int N, int K, const double* A, long long lda, 
         if (!make_map_i8_3d(&mB, B8, K, N, s, ldB, planeB, 128, 128)) return cudaErrorNotSupported;
         p.tiles_m = (M + 255) / 256;
         p.tiles_n = (N + 255) / 256;
-        static bool attr2_done = false;
-        if (!attr2_done) {
+        static std::atomic<bool> attr2_done{false};   // idempotent attribute set; atomic so threads sharing a context may race here
+        if (!attr2_done.load(std::memory_order_acquire)) {
             e = cudaFuncSetAttribute(gemm_ozaki_i8_2cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES);
             if (e != cudaSuccess) return e;
-            attr2_done = true;
+            attr2_done.store(true, std::memory_order_release);
         }
         const int clusters = min(p.tiles_m * p.tiles_n, num_sms / 2);
         gemm_ozaki_i8_2cta_kernel<<<2 * clusters, NUM_THREADS, SMEM2_BYTES, stream>>>(mA, mB, p);
         if (launches) ++*launches;
         return cudaGetLastError();
     }
-    static bool attr_done = false;
-    if (!attr_done) {
+    static std::atomic<bool> attr_done{false};   // idempotent attribute set; atomic so threads sharing a context may race here
+    if (!attr_done.load(std::memory_order_acquire)) {
         e = cudaFuncSetAttribute(gemm_ozaki_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
         if (e != cudaSuccess) return e;
-        attr_done = true;
+        attr_done.store(true, std::memory_order_release);
     }
     const int grid = min(p.tiles_m * p.tiles_n, num_sms);
     gemm_ozaki_i8_kernel<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(mA, mB, p);

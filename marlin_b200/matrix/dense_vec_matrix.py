@@ -229,9 +229,36 @@ class DenseVecMatrix(DistributedMatrix):
         if self.numRows() != other.numRows() or self.numCols() != other.numCols():
             raise nat.MarlinArgumentError(nat.MB_ERR_DIM_MISMATCH, f"Dimension mismatch: {self.numRows()}x{self.numCols()} vs "
                                           f"{other.numRows()}x{other.numCols()}")
-        other = other._aligned_to(self)                                          # rows.join(that.rows)
+        # rows.join(that.rows) (:777-780) is an INNER join: a row id present on one side only is dropped from the result
+        theirs = set(int(i) for part in self._gather([other.ids.tolist()]) for i in part)
+        keep = [p for p, i in enumerate(self.ids) if int(i) in theirs]
+        me = self if len(keep) == len(self.ids) else self._select_rows(keep)
+        if me.data is None or not len(me.ids):
+            other._aligned_to(me)                                                # still collective on every rank
+            return DenseVecMatrix(ids=me.ids, data=me.data, nRows=self.numRows(), nCols=self.numCols())
+        other = other._aligned_to(me)
         fn = {"add": SubMatrix.add, "subtract": SubMatrix.subtract, "dotProduct": SubMatrix.elementMultiply}[op]
-        return DenseVecMatrix(ids=self.ids, data=fn(self.data, other.data), nRows=self.numRows(), nCols=self.numCols())
+        return DenseVecMatrix(ids=me.ids, data=fn(me.data, other.data), nRows=self.numRows(), nCols=self.numCols())
+
+    def _select_rows(self, positions) -> "DenseVecMatrix":
+        """The local rows at `positions` (ascending local order) as a new packed row-major shard."""
+        nc = self.numCols()
+        ids = self.ids[list(positions)] if len(positions) else np.zeros(0, dtype=np.int64)
+        if not len(positions):
+            empty = SubMatrix(buf=torch.zeros(0, dtype=self.data.buf.dtype, device=self.data.buf.device), rows=0, cols=nc,
+                              ld=max(1, nc), is_transpose=True)
+            return DenseVecMatrix(ids=ids, data=empty, nRows=self._nRows, nCols=nc)
+        buf = torch.empty(len(positions) * nc, dtype=self.data.buf.dtype, device=self.data.buf.device)
+        shard = SubMatrix(buf=buf, rows=len(positions), cols=nc, ld=max(1, nc), is_transpose=True)
+        # runs of consecutive positions move as one strided copy
+        p = 0
+        while p < len(positions):
+            q = p
+            while q + 1 < len(positions) and positions[q + 1] == positions[q] + 1:
+                q += 1
+            shard.slice(p, q + 1, 0, nc).assign(self.data.slice(positions[p], positions[q] + 1, 0, nc))
+            p = q + 1
+        return DenseVecMatrix(ids=ids, data=shard, nRows=self._nRows, nCols=nc)
 
     def _aligned_to(self, ref: "DenseVecMatrix") -> "DenseVecMatrix":
         """Re-shard / re-order rows so that they line up with `ref`'s ids (the join on row index)."""

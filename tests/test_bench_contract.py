@@ -24,7 +24,7 @@ def _run(args, env=None, timeout=600):
 
 
 def test_reference_arm_line():
-    d = _run(["--impl", "reference", "--steps", "1", "--warmup", "1", "--cpu-seconds", "1"])
+    d = _run(["--impl", "reference", "--steps", "1", "--warmup", "1", "--ref-seconds", "0.3"])
     assert d["impl"] == "reference" and BASE_KEYS <= set(d)
     assert d["unit"] == "TFLOP/s" and d["higher_is_better"] is True and d["dtype"] == "f64" and d["vs_baseline"] is None
     assert d["value"] > 0 and d["n_gpus"] == 1 and d["steps"] == 1 and d["warmup"] == 1
@@ -32,6 +32,28 @@ def test_reference_arm_line():
     cb = d["cpu_baseline"]
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert cb["extrapolation"]["by"] == "flops" and "median of" in cb["sample"]
+
+
+def test_reference_arm_thread_count_survives_torchrun_env():
+    """torch.distributed.run exports OMP_NUM_THREADS=1 for nproc > 1: the CPU arm must still use (and REPORT) every core the
+    BLAS can drive, so its value is comparable across N (VERDICT r01 weak #5)."""
+    env = dict(os.environ, OMP_NUM_THREADS="1", RANK="0", WORLD_SIZE="8", LOCAL_RANK="0", MASTER_ADDR="127.0.0.1", MASTER_PORT="29998")
+    env.pop("OPENBLAS_NUM_THREADS", None)
+    d = _run(["--impl", "reference", "--gpus", "8", "--steps", "1", "--warmup", "1", "--ref-seconds", "0.3"], env=env)
+    from threadpoolctl import threadpool_info
+    import numpy  # noqa: F401
+    cap = max(i["num_threads"] for i in threadpool_info() if i.get("user_api") == "blas")     # this process: default = all cores
+    assert d["cpu_baseline"]["cores"] == cap and d["cpu_baseline"]["host_cores"] == os.cpu_count()
+    assert f"on {cap} threads" in d["cpu_baseline"]["sample"]
+
+
+def test_both_arms_share_config_and_metric():
+    import bench
+    import argparse
+    a = argparse.Namespace(size=16384, grid=2, workload="blockmatrix", dtype="f64")
+    assert bench.workload_config(a, 8)["workload"] == bench.workload_config(a, 1)["workload"]
+    assert bench.metric_name(a) == bench.METRIC
 
 
 def test_reference_arm_other_ranks_exit_quietly():
@@ -52,6 +74,6 @@ def test_our_arm_fails_loudly_without_gpu():
 
 
 def test_reference_arm_tallskinny_workload():
-    d = _run(["--impl", "reference", "--workload", "tallskinny", "--steps", "1", "--warmup", "1", "--cpu-seconds", "1"])
+    d = _run(["--impl", "reference", "--workload", "tallskinny", "--steps", "1", "--warmup", "1", "--ref-seconds", "0.3"])
     assert "tall-skinny" in d["metric"] and "configs[3]" in d["config"]["workload"]
     assert d["value"] > 0 and "rows" in d["cpu_baseline"]["sample"] and d["cpu_baseline"]["f2j_single_thread"]["cores"] == 1

@@ -359,6 +359,104 @@ def test_matmul_blocked_seq_order(gpu, oracle):
             assert np.abs(got - refb[(i, j)]).max() <= 1e-12
 
 
+def upload_even_ld(gpu, mat):
+    """A column-major device block whose leading dimension is even (TMA eligibility of the DMMA kernels: 16-byte
+    rows), whatever the row count: odd-row matrices become a view [0:rows) of a (rows + 1)-row allocation."""
+    lib, ctx = gpu
+    rows, cols = mat.shape
+    if rows % 2 == 0:
+        return upload_mat(gpu, mat)
+    big = alloc(gpu, rows + 1, cols)
+    view = nat.c_blk()
+    nat.check(lib.mb_block_slice(ctx, big, 0, rows, 0, cols, C.byref(view)))
+    packed = upload_mat(gpu, mat)
+    nat.check(lib.mb_block_copy(ctx, packed, view))
+    nat.check(lib.mb_block_free(ctx, packed))
+    return view
+
+
+@pytest.mark.parametrize("dims", [(1000, 900, 1100, 2, 3, 2), (700, 530, 900, 2, 3, 2), (2048, 2048, 2048, 2, 2, 2),
+                                  (1500, 260, 300, 3, 2, 1), (390, 4100, 650, 1, 4, 2)])
+def test_matmul_blocked_grouped_kernel_multitile_ragged(gpu, oracle, dims):
+    """The headline kernel, gemm_f64_dmma_grouped_kernel, against the oracle on blocks that span SEVERAL 128x128 CTA
+    tiles, with ragged last blocks (ceil sizing, BlockMatrix.scala:73-74), ragged K segments and more than one C block
+    per launch: tile location across C blocks (locate / tile_coords), banding, multi-wave scheduling and the K loop
+    concatenated over kk.  Every tile gets an even leading dimension so the launch IS the grouped one — asserted through
+    the launch counter (one launch for the whole multiply; the per-product fallback would need m*k*n)."""
+    lib, ctx = gpu
+    M, K, N, m, k, n = dims
+    rng = np.random.default_rng(M + K + N)
+    A, B = rng.random((M, K)) - 0.5, rng.random((K, N)) - 0.5
+    oa = oracle.DenseVecMatrix(list(enumerate(A))).to_block_matrix(m, k)
+    ob = oracle.DenseVecMatrix(list(enumerate(B))).to_block_matrix(k, n)
+    ref = dict(oa.multiply(ob, gemm="blas" if M * K * N > 4e8 else "f2j").blocks)
+    ta, tb = dict(oa.blocks), dict(ob.blocks)
+    a_h = (nat.c_blk * (m * k))(*[upload_even_ld(gpu, ta[(i, kk)]) for i in range(m) for kk in range(k)])
+    b_h = (nat.c_blk * (k * n))(*[upload_even_ld(gpu, tb[(kk, j)]) for kk in range(k) for j in range(n)])
+    shapes = {(i, j): (ta[(i, 0)].shape[0], tb[(0, j)].shape[1]) for i in range(m) for j in range(n)}
+    c_h = (nat.c_blk * (m * n))(*[alloc(gpu, *shapes[(i, j)]) for i in range(m) for j in range(n)])
+    for c in c_h:
+        nat.check(lib.mb_block_fill(ctx, c, float("nan")))          # the grouped launch overwrites, never accumulates
+    l0 = lib.mb_launch_count(ctx)
+    nat.check(lib.mb_matmul_blocked(ctx, a_h, b_h, m, k, n, c_h))
+    assert lib.mb_launch_count(ctx) - l0 == 1, "expected ONE grouped launch"
+    worst = 0.0
+    for i in range(m):
+        for j in range(n):
+            got = download(gpu, c_h[i * n + j], *shapes[(i, j)])
+            Ai = np.hstack([ta[(i, kk)] for kk in range(k)])
+            Bj = np.vstack([tb[(kk, j)] for kk in range(k)])
+            e1, e2 = gemm_errors(got, ref[(i, j)], Ai, Bj)
+            assert e1 <= TOL and e2 <= TOL, (i, j, e1, e2)
+            worst = max(worst, e1)
+    # a subset call (two C blocks of the grid) is again one grouped launch and leaves the other blocks untouched
+    if m * n >= 3:
+        for c in c_h:
+            nat.check(lib.mb_block_fill(ctx, c, -7.0))
+        ids = (C.c_int32 * 2)(m * n - 1, 0)
+        l0 = lib.mb_launch_count(ctx)
+        nat.check(lib.mb_matmul_blocked_subset(ctx, a_h, b_h, m, k, n, c_h, ids, 2))
+        assert lib.mb_launch_count(ctx) - l0 == 1
+        for c in range(m * n):
+            i, j = divmod(c, n)
+            got = download(gpu, c_h[c], *shapes[(i, j)])
+            if c in (0, m * n - 1):
+                assert np.abs(got - ref[(i, j)]).max() <= 1e-11
+            else:
+                assert np.all(got == -7.0)
+
+
+def test_matmul_blocked_full_size_freivalds(gpu):
+    """8192^2 on a (2,2,2) grid through mb_matmul_blocked (ONE grouped launch, 4096 CTA tiles = 27.7 waves on 148 SMs, the
+    same tile count per launch as one rank's share of the headline at 8 GPUs): Freivalds — C x == A (B x) with host fp64
+    matvecs on the downloaded tiles, three random vectors, scaled error <= 1e-10 (U[0,1) inputs: |A||B| = A B)."""
+    lib, ctx = gpu
+    g, bs = 2, 4096
+    n = g * bs
+    tiles = {}
+    for name, seed in (("A", 42), ("B", 43)):
+        for r in range(g):
+            for c in range(g):
+                h = alloc(gpu, bs, bs)
+                nat.check(lib.mb_fill_uniform(ctx, h, seed * 1000 + r * g + c, 0, 0.0, 1.0, 0))
+                tiles[(name, r, c)] = h
+    a_h = (nat.c_blk * (g * g))(*[tiles[("A", i, kk)] for i in range(g) for kk in range(g)])
+    b_h = (nat.c_blk * (g * g))(*[tiles[("B", kk, j)] for kk in range(g) for j in range(g)])
+    c_h = (nat.c_blk * (g * g))(*[alloc(gpu, bs, bs) for _ in range(g * g)])
+    l0 = lib.mb_launch_count(ctx)
+    nat.check(lib.mb_matmul_blocked(ctx, a_h, b_h, g, g, g, c_h))
+    assert lib.mb_launch_count(ctx) - l0 == 1
+    full = lambda hs: np.block([[download(gpu, hs[r * g + c], bs, bs) for c in range(g)] for r in range(g)])
+    Ah, Bh, Ch = full(a_h), full(b_h), full(c_h)
+    rng = np.random.default_rng(5)
+    for _ in range(3):
+        x = rng.random(n)
+        lhs, rhs = Ch @ x, Ah @ (Bh @ x)
+        assert (np.abs(lhs - rhs) / rhs).max() <= TOL
+    for h in list(a_h) + list(b_h) + list(c_h):
+        nat.check(lib.mb_block_free(ctx, h))
+
+
 @pytest.mark.parametrize("dims", [(75, 64, 51, 2, 3, 2), (300, 200, 2100, 1, 2, 2), (260, 130, 1100, 1, 1, 1),
                                   (200, 2300, 260, 1, 2, 2), (131, 2111, 77, 2, 2, 1), (140, 1200, 1300, 2, 1, 2)])
 def test_matmul_blocked_host_pipelined(gpu, oracle, dims):

@@ -85,6 +85,24 @@ def test_elementwise(M):                         # :164-205
     assert np.array_equal(ma.subtract(mat).toBreeze(), np.zeros((4, 4)))
 
 
+def test_elementwise_join_drops_unmatched_rows(M):
+    """DenseVecMatrix.add/subtract/dotProduct are `rows.join(that.rows)` (DenseVecMatrix.scala:777-780): an INNER join,
+    so a row id that exists on one side only does not appear in the result (it stays zero in toBreeze())."""
+    rng = np.random.default_rng(4)
+    A, B = rng.random((6, 5)), rng.random((6, 5))
+    a = M.DenseVecMatrix([(i, A[i]) for i in (0, 1, 2, 4, 5)], 6, 5)          # row 3 missing
+    b = M.DenseVecMatrix([(i, B[i]) for i in (5, 3, 2, 1, 0)], 6, 5)          # row 4 missing, other order
+    want = np.zeros((6, 5))
+    for i in (0, 1, 2, 5):
+        want[i] = A[i] + B[i]
+    got = a.add(b)
+    assert sorted(got.ids.tolist()) == [0, 1, 2, 5]
+    assert np.array_equal(got.toBreeze(), want)
+    for i in (0, 1, 2, 5):
+        want[i] = A[i] * B[i]
+    assert np.array_equal(a.dotProduct(b).toBreeze(), want)
+
+
 def test_multiply_selects_broadcast(M):          # :225-234
     mat = dvm(M)
     res = mat.multiply(mat, 2)
