@@ -229,6 +229,33 @@ int32_t mb_flag_signal(mb_ctx* ctx, void* flag, int64_t value);   /* on the ctx 
 int32_t mb_flag_wait(mb_ctx* ctx, const void* flag, int64_t value); /* on the ctx stream: wait until *flag >= value */
 int32_t mb_memcpy_async(mb_ctx* ctx, void* dst, const void* src, int64_t bytes);   /* D2D (local or peer) on the ctx stream */
 
+/* ---- (e) BlockMatrix.multiply across the GPUs of one box, entirely behind this ABI ---------------------------------
+ * One process (or thread with its own ctx) per GPU.  mb_comm is the analogue of the executors of one SparkContext:
+ * created once, collectively, by `world` ranks that pass the same `session` string (unique per communicator: it names a
+ * POSIX shared-memory segment used for rendezvous and per-call tile directories — no network, no torch, no MPI).
+ * mb_matmul_blocked_dist is the whole of matrix/BlockMatrix.scala:159-178 — MatrixMultPartitioner mapping
+ * (seq = i*n*k + j*k + kk dealt to ranks in contiguous ranges: mb_dist_plan), tile replication (NVLink peer-memory
+ * pulls overlapped with the products), the m*k*n DMMA block products (one persistent launch per rank) and the
+ * reduceByKey of the k partials (fused GEMM + reduce-scatter between two holders, staged adds otherwise).
+ * Every rank calls it with the same m, k, n, lengths and owner maps; A_tiles[i*k+kk] / B_tiles[kk*n+j] are non-NULL
+ * exactly where the owner map names this rank; C_tiles[i*n+j] must be a preallocated (row_len[i] x col_len[j]) block
+ * (F64, or F32 for BF16 inputs) wherever mb_dist_plan's c_owner names this rank, and receives the finished tile there.
+ * Asynchronous like every other compute entry: ordered on the ctx stream. */
+typedef struct mb_comm mb_comm;
+#define MB_ERR_TIMEOUT       -7   /* a peer did not answer within MARLIN_B200_TIMEOUT_S (default 120 s) -> RuntimeException */
+int32_t mb_comm_init(mb_ctx* ctx, int32_t rank, int32_t world, const char* session, mb_comm** out);
+int32_t mb_comm_destroy(mb_comm* comm);
+int32_t mb_comm_rank(const mb_comm* comm);
+int32_t mb_comm_world(const mb_comm* comm);
+int32_t mb_comm_barrier(mb_comm* comm);            /* host-side barrier of the ranks */
+int32_t mb_comm_check(mb_comm* comm);              /* MB_ERR_TIMEOUT if a device-side wait for a peer ever gave up */
+/* MatrixMultPartitioner + placement: product seq -> rank (m*k*n entries) and C tile -> owning rank (m*n entries). */
+int32_t mb_dist_plan(int32_t m, int32_t k, int32_t n, int32_t world, int32_t* product_rank_out, int32_t* c_owner_out);
+int32_t mb_matmul_blocked_dist(mb_comm* comm, mb_block* const* A_tiles, const int32_t* a_owner,
+                               mb_block* const* B_tiles, const int32_t* b_owner, int32_t m, int32_t k, int32_t n,
+                               const int32_t* row_len, const int32_t* k_len, const int32_t* col_len, int32_t dtype,
+                               mb_block* const* C_tiles);
+
 /* ---- rows <-> blocks on device (matrix/DenseVecMatrix.scala:1084-1223, 1259-1328;
  *      matrix/BlockMatrix.scala:575-594): a DenseVecMatrix shard is a row-major (rows x cols)
  *      buffer, i.e. a transposed block; these are strided copies (mb_block_copy on views). */

@@ -17,6 +17,7 @@ MB_ERR_UNSUPPORTED = -3
 MB_ERR_CUDA = -4
 MB_ERR_OOM = -5
 MB_ERR_EMPTY = -6
+MB_ERR_TIMEOUT = -7
 
 MB_F64, MB_BF16, MB_F32 = 0, 1, 2
 
@@ -93,6 +94,15 @@ SIGNATURES = {
     "mb_matmul_blocked_subset": (c_i32, [c_ctx, C.POINTER(c_blk), C.POINTER(c_blk), c_i32, c_i32, c_i32, C.POINTER(c_blk),
                                          C.POINTER(c_i32), c_i32]),
     "mb_matmul_blocked": (c_i32, [c_ctx, C.POINTER(c_blk), C.POINTER(c_blk), c_i32, c_i32, c_i32, C.POINTER(c_blk)]),
+    "mb_comm_init": (c_i32, [c_ctx, c_i32, c_i32, C.c_char_p, C.POINTER(C.c_void_p)]),
+    "mb_comm_destroy": (c_i32, [C.c_void_p]),
+    "mb_comm_rank": (c_i32, [C.c_void_p]),
+    "mb_comm_world": (c_i32, [C.c_void_p]),
+    "mb_comm_barrier": (c_i32, [C.c_void_p]),
+    "mb_comm_check": (c_i32, [C.c_void_p]),
+    "mb_dist_plan": (c_i32, [c_i32, c_i32, c_i32, c_i32, C.POINTER(c_i32), C.POINTER(c_i32)]),
+    "mb_matmul_blocked_dist": (c_i32, [C.c_void_p, C.POINTER(c_blk), C.POINTER(c_i32), C.POINTER(c_blk), C.POINTER(c_i32), c_i32, c_i32,
+                                       c_i32, C.POINTER(c_i32), C.POINTER(c_i32), C.POINTER(c_i32), c_i32, C.POINTER(c_blk)]),
 }
 
 

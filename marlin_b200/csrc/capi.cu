@@ -19,92 +19,11 @@
 #include <mutex>
 #include <vector>
 
-struct mb_ctx {
-    int device = 0;
-    int num_sms = 148;
-    cudaStream_t own_stream = nullptr;
-    cudaStream_t stream = nullptr;
-    std::atomic<long long> launches{0};
-    double* scratch = nullptr;          // sum partials + result
-    double* host_scalar = nullptr;      // pinned
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    // pipelined host<->device path (mb_matmul_blocked_host): copy streams + a grow-only device workspace
-    cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
-    void* workspace = nullptr;
-    size_t workspace_bytes = 0;
-    // fp64 mode (mb_set_fp64_mode) and the digit-plane workspace of the int8-split path
-    int fp64_mode = MB_FP64_NATIVE;
-    int fp64_slices = 7;
-    int fp64_bits = 7;
-    void* ozaki_ws = nullptr;
-    size_t ozaki_ws_bytes = 0;
-    // partial vectors of the matrix x vector kernels (grow-only)
-    double* vec_ws = nullptr;
-    size_t vec_ws_doubles = 0;
-    // Entry points that use the context's own scratch buffers, workspaces, events or copy streams take this lock, so
-    // threads sharing one context (Spark local[N] task threads) serialise there; kernel-only entries (gemm, element-wise,
-    // transpose, fill) touch no shared host state and need none.  Threads that want concurrency use one context each.
-    std::recursive_mutex mu;
-};
-
-struct mb_block {
-    void* data = nullptr;      // device base pointer (element 0 of the underlying array)
-    long long offset = 0;      // in elements
-    int rows = 0, cols = 0;    // logical dims
-    int ld = 0;                // majorStride
-    int is_transpose = 0;
-    int dtype = MB_F64;
-    int owns = 0;
-    int device = 0;
-};
-
-namespace mb {
-cudaError_t ipc_export(const void* dptr, unsigned char handle[64], long long* offset, long long* alloc_bytes);
-cudaError_t ipc_open(const unsigned char handle[64], void** base_out);
-cudaError_t ipc_close_all();
-cudaError_t flag_signal(void* flag, unsigned long long v, cudaStream_t st);
-cudaError_t flag_wait(const void* flag, unsigned long long v, cudaStream_t st);
-}  // namespace mb
+#include "internal.h"
 
 namespace {
 
 thread_local char g_err[512] = "";
-
-int32_t fail(int32_t code, const char* fmt, ...) {
-    va_list ap;
-    va_start(ap, fmt);
-    vsnprintf(g_err, sizeof(g_err), fmt, ap);
-    va_end(ap);
-    return code;
-}
-int32_t cuda_fail(cudaError_t e, const char* what) {
-    return fail(e == cudaErrorMemoryAllocation ? MB_ERR_OOM : MB_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
-}
-#define MB_CUDA(call)                                       \
-    do {                                                    \
-        cudaError_t _e = (call);                            \
-        if (_e != cudaSuccess) return cuda_fail(_e, #call); \
-    } while (0)
-
-inline size_t elem_size(int dtype) { return dtype == MB_F64 ? 8 : (dtype == MB_F32 ? 4 : 2); }
-inline char* elem_ptr(const mb_block* b) { return static_cast<char*>(b->data) + b->offset * (long long)elem_size(b->dtype); }
-inline double* f64_ptr(const mb_block* b) { return reinterpret_cast<double*>(elem_ptr(b)); }
-// strides of the logical (rows x cols) view
-inline long long rs(const mb_block* b) { return b->is_transpose ? b->ld : 1; }
-inline long long cs(const mb_block* b) { return b->is_transpose ? 1 : b->ld; }
-
-int32_t check_ctx(mb_ctx* ctx) {
-    if (!ctx) return fail(MB_ERR_INVALID_ARG, "null context");
-    cudaError_t e = cudaSetDevice(ctx->device);
-    if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
-    return MB_OK;
-}
-#define MB_CTX(ctx)                        \
-    do {                                   \
-        int32_t _r = check_ctx(ctx);       \
-        if (_r != MB_OK) return _r;        \
-    } while (0)
-#define MB_LOCK(ctx) std::lock_guard<std::recursive_mutex> _mb_lock((ctx)->mu)
 
 int32_t new_block(mb_block** out) {
     *out = new (std::nothrow) mb_block();
@@ -211,6 +130,14 @@ bool as_vector(const mb_block* b, vec_view* v) {
 }
 
 }  // namespace
+
+int32_t mb_fail(int32_t code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
 
 extern "C" {
 

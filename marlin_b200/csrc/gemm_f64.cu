@@ -253,37 +253,93 @@ gemm_f64_dmma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
 }
 
 // -------------------------------------------------------------------------------------------
-// Grouped variant: ONE persistent launch for a whole blocked multiply on this GPU
-// (BlockMatrix.multiply, matrix/BlockMatrix.scala:149-186): the CTA-tile list spans every C block (i,j) this rank
-// owns, and each CTA-tile runs its K loop over the concatenation kk = 0..k-1 of A(i,kk) / B(kk,j), i.e. the
-// reduceByKey over kk (:177) happens in the register accumulators.  Compared with one launch per block product
-// this removes the per-launch tail (4096 tiles on 148 SMs = 27.7 waves) and the C read-modify-write of accumulate.
-// All operands are 'N' (column-major blocks).
+// Grouped variant: ONE persistent launch for a rank's whole share of a blocked multiply
+// (BlockMatrix.multiply, matrix/BlockMatrix.scala:149-186).  The launch is a list of ENTRIES; an entry is a rectangular
+// region of one C block (i,j) — the whole block, a column half, or a (row band x column band) sub-block — with its own
+// list of K segments (the kk this rank holds, each an A(i,kk) / B(kk,j) pair), so the reduceByKey over kk (:177)
+// happens in the register accumulators and the 27.7-wave tail of a per-product launch is paid once per launch, not
+// once per product.  All operands are 'N' (column-major blocks).
+//
+// Three things make the same kernel the compute half of the multi-GPU protocol (csrc/dist.cu):
+//   * operand readiness: an operand tile may still be in flight (copy-engine pull over NVLink, or H2D upload) when
+//     the kernel starts.  The TMA producer thread polls a per-(tile, band) flag (ld.acquire.gpu) before the first
+//     load that touches the band, so the tensor cores start on the bands that have landed;
+//   * an entry may add a staged addend: D = acc + Cin, gated by a system-scope flag (the other holder of the C block
+//     has finished writing its partial into this GPU's staging buffer), and D may be a PEER pointer: the epilogue's
+//     st.global.v2.f64 go over NVLink.  Together: GEMM + reduce-scatter of the k partials in one kernel;
+//   * completion: when the last CTA tile of an entry has been stored, one thread publishes a flag (st.release.sys)
+//     locally (the D2H stream waits on it) and/or on the peer (its gated entries may start).
 // -------------------------------------------------------------------------------------------
-constexpr int GROUP_MAX_A = 16, GROUP_MAX_B = 16, GROUP_MAX_C = 16, GROUP_MAX_K = 16;
-
-struct GroupedParams {
-    CUtensorMap mapA[GROUP_MAX_A];     // index a_idx[c] + kk   (the A block row of C block c, kk ascending)
-    CUtensorMap mapB[GROUP_MAX_B];     // index b_idx[c] + kk
-    double* C[GROUP_MAX_C];
-    long long ldc[GROUP_MAX_C];
-    int M[GROUP_MAX_C], N[GROUP_MAX_C];
-    int a_idx[GROUP_MAX_C], b_idx[GROUP_MAX_C];
-    int tile_start[GROUP_MAX_C + 1];   // prefix sum of CTA-tiles per C block
-    int tiles_m[GROUP_MAX_C], tiles_n[GROUP_MAX_C];
-    int num_c, k;
-    int num_kb[GROUP_MAX_K];           // k-slabs of segment kk
+struct G2Ent {
+    double* D;
+    const double* Cin;
+    const unsigned long long* cin_flag;
+    unsigned long long cin_val;
+    unsigned long long* done_ctr;
+    unsigned long long* sig_remote;
+    unsigned long long* sig_local;
+    unsigned long long sig_val;
+    long long ldd, ldcin;
+    int M, N, m_off, n_off;
+    int tiles_m, tiles_n, tile_start, nseg;
+    unsigned short nkb[G2_MAX_SEG];
+    unsigned char a_op[G2_MAX_SEG], b_op[G2_MAX_SEG];
 };
 
+struct G2Params {
+    CUtensorMap mapA[G2_MAX_OPS];
+    CUtensorMap mapB[G2_MAX_OPS];
+    G2Ent e[G2_MAX_ENTRIES];
+    int a_band[G2_MAX_OPS], b_band[G2_MAX_OPS];          // rows (A) / columns (B) per readiness band
+    short a_ready[G2_MAX_OPS], b_ready[G2_MAX_OPS];      // first flag of the tile in `ready`, or -1 = resident
+    const unsigned long long* ready;
+    unsigned long long ready_val;
+    unsigned long long* status;                           // set to 1 if a wait times out
+    long long timeout_ns;
+    int ne, num_tiles;
+};
+
+__device__ __forceinline__ unsigned long long ld_acquire_gpu(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// Spin until *flag >= v.  Bounded: after timeout_ns the status word is set and the wait gives up (the result is then
+// garbage, the host sees the status word and reports MB_ERR_TIMEOUT instead of hanging the GPU).
+template <bool SYS>
+__device__ __forceinline__ void wait_flag_ge(const unsigned long long* flag, unsigned long long v, long long timeout_ns,
+                                             unsigned long long* status) {
+    if ((SYS ? ld_acquire_sys(flag) : ld_acquire_gpu(flag)) >= v) return;
+    const unsigned long long t0 = globaltimer_ns();
+    for (unsigned spins = 0;; ++spins) {
+        if ((SYS ? ld_acquire_sys(flag) : ld_acquire_gpu(flag)) >= v) return;
+        __nanosleep(64);
+        if ((spins & 255u) == 255u && timeout_ns > 0 && (long long)(globaltimer_ns() - t0) > timeout_ns) {
+            if (status) *status = 1ull;
+            return;
+        }
+    }
+}
+
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-gemm_f64_dmma_grouped_kernel(const __grid_constant__ GroupedParams g) {
+gemm_f64_dmma_grouped_kernel(const __grid_constant__ G2Params g) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t bar_full = smem_base + NUM_STAGES * STAGE_BYTES;
     const uint32_t bar_empty = bar_full + NUM_STAGES * 8;
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int num_tiles = g.tile_start[g.num_c];
+    const int num_tiles = g.num_tiles;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < NUM_STAGES; ++s) {
@@ -296,8 +352,8 @@ gemm_f64_dmma_grouped_kernel(const __grid_constant__ GroupedParams g) {
 
     auto locate = [&](int t, int& c, int& tm, int& tn) {
         c = 0;
-        while (t >= g.tile_start[c + 1]) ++c;
-        tile_coords(t - g.tile_start[c], g.tiles_m[c], g.tiles_n[c], tm, tn);
+        while (c + 1 < g.ne && t >= g.e[c + 1].tile_start) ++c;
+        tile_coords(t - g.e[c].tile_start, g.e[c].tiles_m, g.e[c].tiles_n, tm, tn);
     };
 
     if (warp < 4) {
@@ -308,11 +364,18 @@ gemm_f64_dmma_grouped_kernel(const __grid_constant__ GroupedParams g) {
             for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
                 int c, tm, tn;
                 locate(t, c, tm, tn);
-                const int m0 = tm * BM, n0 = tn * BN;
-                for (int kk = 0; kk < g.k; ++kk) {
-                    const CUtensorMap* mA = &g.mapA[g.a_idx[c] + kk];
-                    const CUtensorMap* mB = &g.mapB[g.b_idx[c] + kk];
-                    const int nkb = g.num_kb[kk];
+                const G2Ent& en = g.e[c];
+                const int m0 = en.m_off + tm * BM, n0 = en.n_off + tn * BN;
+                for (int sg = 0; sg < en.nseg; ++sg) {
+                    const int ia = en.a_op[sg], ib = en.b_op[sg];
+                    // operand bands still in flight?  (pulled / uploaded tiles only; resident tiles have ready = -1)
+                    if (g.a_ready[ia] >= 0)
+                        wait_flag_ge<false>(g.ready + g.a_ready[ia] + m0 / g.a_band[ia], g.ready_val, g.timeout_ns, g.status);
+                    if (g.b_ready[ib] >= 0)
+                        wait_flag_ge<false>(g.ready + g.b_ready[ib] + n0 / g.b_band[ib], g.ready_val, g.timeout_ns, g.status);
+                    const CUtensorMap* mA = &g.mapA[ia];
+                    const CUtensorMap* mB = &g.mapB[ib];
+                    const int nkb = en.nkb[sg];
                     for (int kb = 0; kb < nkb; ++kb) {
                         mbar_wait(bar_empty + 8 * stage, phase ^ 1);
                         const uint32_t full = bar_full + 8 * stage;
@@ -348,15 +411,17 @@ gemm_f64_dmma_grouped_kernel(const __grid_constant__ GroupedParams g) {
         }
         offB[h] = warp_n * 32 * 128 + pr * 128 + ((((4 * h + q) ^ pr) & 7) << 4);
     }
-    int total_kb = 0;
-    for (int kk = 0; kk < g.k; ++kk) total_kb += g.num_kb[kk];
 
     int stage = 0;
     uint32_t phase = 0;
+    const unsigned long long* cin_seen = nullptr;      // last addend flag this thread has already observed
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
         int c, tm_, tn_;
         locate(t, c, tm_, tn_);
-        const int m0 = tm_ * BM, n0 = tn_ * BN;
+        const G2Ent& en = g.e[c];
+        const int m0 = tm_ * BM, n0 = tn_ * BN;       // relative to the entry's region
+        int total_kb = 0;
+        for (int sg = 0; sg < en.nseg; ++sg) total_kb += en.nkb[sg];
         double acc[8][4][2];
 #pragma unroll
         for (int i = 0; i < 8; ++i)
@@ -390,28 +455,60 @@ gemm_f64_dmma_grouped_kernel(const __grid_constant__ GroupedParams g) {
             if (++stage == NUM_STAGES) { stage = 0; phase ^= 1; }
         }
 
-        double* Cb = g.C[c];
-        const long long ldc = g.ldc[c];
-        const int Mc = g.M[c], Nc = g.N[c];
-        const bool vec_ok = ((reinterpret_cast<uintptr_t>(Cb) & 15) == 0) && ((ldc & 1) == 0);
+        // ---------------- epilogue: D = acc (+ Cin) ----------------
+        double* Db = en.D;
+        const double* Ci = en.Cin;
+        const long long ldd = en.ldd, ldci = en.ldcin;
+        const int Mc = en.M, Nc = en.N;
+        if (Ci != nullptr && en.cin_flag != nullptr && en.cin_flag != cin_seen) {
+            // the other holder's partial must have landed in this GPU's staging buffer (every lane acquires)
+            wait_flag_ge<true>(en.cin_flag, en.cin_val, g.timeout_ns, g.status);
+            cin_seen = en.cin_flag;
+        }
+        const bool vec_ok = ((reinterpret_cast<uintptr_t>(Db) & 15) == 0) && ((ldd & 1) == 0) &&
+                            (Ci == nullptr || (((reinterpret_cast<uintptr_t>(Ci) & 15) == 0) && ((ldci & 1) == 0)));
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
 #pragma unroll
             for (int jj = 0; jj < 2; ++jj) {
                 const int n = n0 + warp_n * 32 + 8 * j + perm8(2 * q + jj);
                 if (n >= Nc) continue;
-                double* ccol = Cb + (long long)n * ldc;
+                double* dcol = Db + (long long)n * ldd;
+                const double* ccol = Ci ? Ci + (long long)n * ldci : nullptr;
 #pragma unroll
                 for (int tp = 0; tp < 4; ++tp) {
                     const int m = m0 + warp_m * 64 + 16 * tp + 2 * r;
                     if (m >= Mc) continue;
-                    const double v0 = acc[2 * tp][j][jj], v1 = acc[2 * tp + 1][j][jj];
+                    double v0 = acc[2 * tp][j][jj], v1 = acc[2 * tp + 1][j][jj];
                     if (vec_ok && m + 1 < Mc) {
-                        *reinterpret_cast<double2*>(ccol + m) = make_double2(v0, v1);
+                        if (ccol) {
+                            const double2 old = __ldcg(reinterpret_cast<const double2*>(ccol + m));
+                            v0 += old.x;
+                            v1 += old.y;
+                        }
+                        *reinterpret_cast<double2*>(dcol + m) = make_double2(v0, v1);
                     } else {
-                        ccol[m] = v0;
-                        if (m + 1 < Mc) ccol[m + 1] = v1;
+                        if (ccol) v0 += __ldcg(ccol + m);
+                        dcol[m] = v0;
+                        if (m + 1 < Mc) {
+                            if (ccol) v1 += __ldcg(ccol + m + 1);
+                            dcol[m + 1] = v1;
+                        }
                     }
+                }
+            }
+        }
+        if (en.done_ctr != nullptr) {
+            // every consumer thread's stores of this tile, then ONE thread counts the tile and, if it was the entry's last,
+            // publishes the completion flags with system scope (peer GPUs and the copy streams poll them)
+            asm volatile("bar.sync 1, %0;" ::"n"(NUM_CONSUMER_WARPS * 32) : "memory");
+            if (cw == 0 && lane == 0) {
+                __threadfence_system();
+                const unsigned long long prev = atomicAdd(en.done_ctr, 1ull);
+                if (prev + 1ull == (unsigned long long)(en.tiles_m * en.tiles_n)) {
+                    __threadfence_system();
+                    if (en.sig_remote) asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(en.sig_remote), "l"(en.sig_val) : "memory");
+                    if (en.sig_local) asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(en.sig_local), "l"(en.sig_val) : "memory");
                 }
             }
         }
@@ -588,24 +685,77 @@ cudaError_t gemm_f64(bool transA, bool transB, int M, int N, int K, double alpha
 }
 
 
+cudaError_t gemm_f64_grouped2(const G2Launch& L, int num_sms, cudaStream_t stream, int* launches) {
+    if (L.ne <= 0) return cudaSuccess;
+    if (L.ne > G2_MAX_ENTRIES || L.na > G2_MAX_OPS || L.nb > G2_MAX_OPS || !get_encode_fn()) return cudaErrorNotSupported;
+    static thread_local G2Params g;          // ~20 KB parameter block: kept off the stack, one per calling thread
+    for (int i = 0; i < L.na; ++i) {
+        const G2Operand& o = L.A[i];
+        if (o.rows <= 0 || o.cols <= 0 || !gemm_f64_tma_eligible(o.ptr, o.ld, o.ptr, 2)) return cudaErrorNotSupported;
+        if (!make_map_f64(&g.mapA[i], o.ptr, o.rows, o.cols, o.ld, 16, 16)) return cudaErrorNotSupported;
+        if (o.ready_base >= 0 && (o.band <= 0 || o.band % BM != 0)) return cudaErrorInvalidValue;
+        g.a_band[i] = o.band > 0 ? o.band : (1 << 30);
+        g.a_ready[i] = (short)o.ready_base;
+    }
+    for (int i = 0; i < L.nb; ++i) {
+        const G2Operand& o = L.B[i];
+        if (o.rows <= 0 || o.cols <= 0 || !gemm_f64_tma_eligible(o.ptr, o.ld, o.ptr, 2)) return cudaErrorNotSupported;
+        if (!make_map_f64(&g.mapB[i], o.ptr, o.rows, o.cols, o.ld, 16, 128)) return cudaErrorNotSupported;
+        if (o.ready_base >= 0 && (o.band <= 0 || o.band % BN != 0)) return cudaErrorInvalidValue;
+        g.b_band[i] = o.band > 0 ? o.band : (1 << 30);
+        g.b_ready[i] = (short)o.ready_base;
+    }
+    int tiles = 0;
+    for (int c = 0; c < L.ne; ++c) {
+        const G2Entry& s = L.E[c];
+        G2Ent& d = g.e[c];
+        if (s.nseg <= 0 || s.nseg > G2_MAX_SEG || s.M <= 0 || s.N <= 0) return cudaErrorNotSupported;
+        if ((s.m_off % BM) != 0 || (s.n_off % BN) != 0) return cudaErrorInvalidValue;
+        d.D = s.D; d.ldd = s.ldd; d.Cin = s.Cin; d.ldcin = s.ldcin;
+        d.cin_flag = s.cin_flag; d.cin_val = s.cin_val;
+        d.done_ctr = s.done_ctr; d.sig_remote = s.sig_remote; d.sig_local = s.sig_local; d.sig_val = s.sig_val;
+        d.M = s.M; d.N = s.N; d.m_off = s.m_off; d.n_off = s.n_off;
+        d.tiles_m = (s.M + BM - 1) / BM;
+        d.tiles_n = (s.N + BN - 1) / BN;
+        d.tile_start = tiles;
+        tiles += d.tiles_m * d.tiles_n;
+        d.nseg = s.nseg;
+        for (int sg = 0; sg < s.nseg; ++sg) {
+            const int ia = s.a_op[sg], ib = s.b_op[sg];
+            if (ia < 0 || ia >= L.na || ib < 0 || ib >= L.nb || L.A[ia].cols != L.B[ib].rows) return cudaErrorInvalidValue;
+            const int nkb = (L.A[ia].cols + BK - 1) / BK;
+            if (nkb > 65535) return cudaErrorNotSupported;
+            d.nkb[sg] = (unsigned short)nkb;
+            d.a_op[sg] = (unsigned char)ia;
+            d.b_op[sg] = (unsigned char)ib;
+        }
+    }
+    g.ready = L.ready; g.ready_val = L.ready_val; g.status = L.status; g.timeout_ns = L.timeout_ns;
+    g.ne = L.ne;
+    g.num_tiles = tiles;
+    static std::atomic<bool> attr_done{false};
+    if (!attr_done.load(std::memory_order_acquire)) {
+        cudaError_t e = cudaFuncSetAttribute(gemm_f64_dmma_grouped_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+        attr_done.store(true, std::memory_order_release);
+    }
+    const int grid = min(tiles, num_sms);
+    gemm_f64_dmma_grouped_kernel<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(g);
+    if (launches) ++*launches;
+    return cudaGetLastError();
+}
+
 cudaError_t gemm_f64_grouped(int m, int k, int n, const int* my_c, int num_c, const double* const* A, const long long* lda,
                              const double* const* B, const long long* ldb, double* const* C, const long long* ldc,
                              const int* row_len, const int* k_len, const int* col_len, int num_sms, cudaStream_t stream,
                              int* launches) {
-    // my_c: the (i*n + j) ids of the C blocks to compute; A[i*k+kk], B[kk*n+j], C[i*n+j] column-major 'N' blocks
+    // my_c: the (i*n + j) ids of the C blocks to compute; A[i*k+kk], B[kk*n+j], C[i*n+j] column-major 'N' blocks.
+    // One entry per C block (the whole block, every kk), operands resident: no flags, no addend.
     if (num_c <= 0) return cudaSuccess;
-    if (num_c > GROUP_MAX_C || k > GROUP_MAX_K || !get_encode_fn()) return cudaErrorNotSupported;
-    static thread_local GroupedParams g;     // ~4.6 KB parameter block: kept off the stack, one per calling thread
-    int na = 0, nb = 0;
-    int a_of_row[GROUP_MAX_C], b_of_col[GROUP_MAX_C];
-    int rows_seen[GROUP_MAX_C], cols_seen[GROUP_MAX_C], nrows = 0, ncols = 0;
-    g.num_c = num_c;
-    g.k = k;
-    for (int kk = 0; kk < k; ++kk) {
-        if (k_len[kk] <= 0) return cudaErrorNotSupported;
-        g.num_kb[kk] = (k_len[kk] + BK - 1) / BK;
-    }
-    g.tile_start[0] = 0;
+    if (num_c > G2_MAX_ENTRIES || k > G2_MAX_SEG) return cudaErrorNotSupported;
+    static thread_local G2Launch L;
+    L = G2Launch();
+    int a_of_row[G2_MAX_ENTRIES], b_of_col[G2_MAX_ENTRIES], rows_seen[G2_MAX_ENTRIES], cols_seen[G2_MAX_ENTRIES], nrows = 0, ncols = 0;
     for (int c = 0; c < num_c; ++c) {
         const int i = my_c[c] / n, j = my_c[c] % n;
         if (row_len[i] <= 0 || col_len[j] <= 0) return cudaErrorNotSupported;
@@ -613,43 +763,29 @@ cudaError_t gemm_f64_grouped(int m, int k, int n, const int* my_c, int num_c, co
         for (int x = 0; x < nrows; ++x) if (rows_seen[x] == i) ri = x;
         for (int x = 0; x < ncols; ++x) if (cols_seen[x] == j) cj = x;
         if (ri < 0) {
-            if (na + k > GROUP_MAX_A) return cudaErrorNotSupported;
+            if (L.na + k > G2_MAX_OPS) return cudaErrorNotSupported;
             for (int kk = 0; kk < k; ++kk) {
-                const double* Ap = A[i * k + kk];
-                if (!gemm_f64_tma_eligible(Ap, lda[i * k + kk], Ap, 2)) return cudaErrorNotSupported;
-                if (!make_map_f64(&g.mapA[na + kk], Ap, row_len[i], k_len[kk], lda[i * k + kk], 16, 16)) return cudaErrorNotSupported;
+                if (k_len[kk] <= 0) return cudaErrorNotSupported;
+                G2Operand& o = L.A[L.na + kk];
+                o.ptr = A[i * k + kk]; o.ld = lda[i * k + kk]; o.rows = row_len[i]; o.cols = k_len[kk]; o.band = 0; o.ready_base = -1;
             }
-            rows_seen[nrows] = i; a_of_row[nrows] = na; ri = nrows++; na += k;
+            rows_seen[nrows] = i; a_of_row[nrows] = L.na; ri = nrows++; L.na += k;
         }
         if (cj < 0) {
-            if (nb + k > GROUP_MAX_B) return cudaErrorNotSupported;
+            if (L.nb + k > G2_MAX_OPS) return cudaErrorNotSupported;
             for (int kk = 0; kk < k; ++kk) {
-                const double* Bp = B[kk * n + j];
-                if (!gemm_f64_tma_eligible(Bp, ldb[kk * n + j], Bp, 2)) return cudaErrorNotSupported;
-                if (!make_map_f64(&g.mapB[nb + kk], Bp, k_len[kk], col_len[j], ldb[kk * n + j], 16, 128)) return cudaErrorNotSupported;
+                G2Operand& o = L.B[L.nb + kk];
+                o.ptr = B[kk * n + j]; o.ld = ldb[kk * n + j]; o.rows = k_len[kk]; o.cols = col_len[j]; o.band = 0; o.ready_base = -1;
             }
-            cols_seen[ncols] = j; b_of_col[ncols] = nb; cj = ncols++; nb += k;
+            cols_seen[ncols] = j; b_of_col[ncols] = L.nb; cj = ncols++; L.nb += k;
         }
-        g.a_idx[c] = a_of_row[ri];
-        g.b_idx[c] = b_of_col[cj];
-        g.C[c] = C[my_c[c]];
-        g.ldc[c] = ldc[my_c[c]];
-        g.M[c] = row_len[i];
-        g.N[c] = col_len[j];
-        g.tiles_m[c] = (row_len[i] + BM - 1) / BM;
-        g.tiles_n[c] = (col_len[j] + BN - 1) / BN;
-        g.tile_start[c + 1] = g.tile_start[c] + g.tiles_m[c] * g.tiles_n[c];
+        G2Entry& e = L.E[L.ne++];
+        e.nseg = k;
+        for (int kk = 0; kk < k; ++kk) { e.a_op[kk] = a_of_row[ri] + kk; e.b_op[kk] = b_of_col[cj] + kk; }
+        e.M = row_len[i]; e.N = col_len[j];
+        e.D = C[my_c[c]]; e.ldd = ldc[my_c[c]];
     }
-    static std::atomic<bool> attr_done{false};
-    if (!attr_done.load(std::memory_order_acquire)) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_f64_dmma_grouped_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-        if (e != cudaSuccess) return e;
-        attr_done.store(true, std::memory_order_release);
-    }
-    const int grid = min(g.tile_start[num_c], num_sms);
-    gemm_f64_dmma_grouped_kernel<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(g);
-    if (launches) ++*launches;
-    return cudaGetLastError();
+    return gemm_f64_grouped2(L, num_sms, stream, launches);
 }
 
 }  // namespace mb

@@ -20,12 +20,24 @@ __global__ void flag_signal_kernel(unsigned long long* flag, unsigned long long 
     __threadfence_system();
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(flag), "l"(v) : "memory");
 }
-__global__ void flag_wait_kernel(const unsigned long long* flag, unsigned long long v) {
-    unsigned long long cur;
-    for (;;) {
+// Bounded wait: after timeout_ns (0 = forever) the kernel sets *status = 2 and returns, so a rank whose peer died
+// mid-multiply gets an error code from the next mb_comm_check / multiply call instead of a GPU that cannot be interrupted.
+__global__ void flag_wait_kernel(const unsigned long long* flag, unsigned long long v, long long timeout_ns,
+                                 unsigned long long* status) {
+    unsigned long long cur, t0 = 0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (unsigned spins = 0;; ++spins) {
         asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(cur) : "l"(flag) : "memory");
         if (cur >= v) break;
         __nanosleep(256);
+        if ((spins & 1023u) == 1023u && timeout_ns > 0) {
+            unsigned long long now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if ((long long)(now - t0) > timeout_ns) {
+                if (status) *status = 2ull;
+                break;
+            }
+        }
     }
 }
 
@@ -78,6 +90,17 @@ cudaError_t ipc_open(const unsigned char handle[64], void** base_out) {
     return cudaSuccess;
 }
 
+// Unmap one peer allocation (the exporter is about to free it, e.g. a staging buffer being regrown).
+cudaError_t ipc_close(const unsigned char handle[64]) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    std::string key(reinterpret_cast<const char*>(handle), 64);
+    auto it = g_opened.find(key);
+    if (it == g_opened.end()) return cudaSuccess;
+    cudaError_t e = cudaIpcCloseMemHandle(it->second);
+    g_opened.erase(it);
+    return e;
+}
+
 cudaError_t ipc_close_all() {
     std::lock_guard<std::mutex> lk(g_mu);
     for (auto& kv : g_opened) cudaIpcCloseMemHandle(kv.second);
@@ -90,7 +113,12 @@ cudaError_t flag_signal(void* flag, unsigned long long v, cudaStream_t st) {
     return cudaGetLastError();
 }
 cudaError_t flag_wait(const void* flag, unsigned long long v, cudaStream_t st) {
-    flag_wait_kernel<<<1, 1, 0, st>>>(static_cast<const unsigned long long*>(flag), v);
+    flag_wait_kernel<<<1, 1, 0, st>>>(static_cast<const unsigned long long*>(flag), v, 0, nullptr);
+    return cudaGetLastError();
+}
+cudaError_t flag_wait_bounded(const void* flag, unsigned long long v, long long timeout_ns, unsigned long long* status,
+                              cudaStream_t st) {
+    flag_wait_kernel<<<1, 1, 0, st>>>(static_cast<const unsigned long long*>(flag), v, timeout_ns, status);
     return cudaGetLastError();
 }
 

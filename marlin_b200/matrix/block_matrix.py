@@ -295,183 +295,45 @@ class BlockMatrix(DistributedMatrix):
         return BlockMatrix(result, M, N, m, n, placement=(lambda r, c, o=owners: o[(r, c)]) if ws > 1 else None)
 
     # ------------------------------------------------------------------ NVLink peer-memory path
-    def _peer_directory(self, mesh, local: dict):
-        """{(row, col): (owner rank, ipc record)} of this matrix's packed tiles; exchanged once and cached."""
-        if getattr(self, "_peer_dir", None) is None:
-            d = peer.tile_directory(mesh, "T", local)
-            self._peer_dir = False if d is None else {key[1:]: v for key, v in d.items()}
-        return self._peer_dir or None
-
     def _multiply_p2p(self, other: "BlockMatrix", mesh, plan, a_local: dict, b_local: dict) -> Optional["BlockMatrix"]:
-        """The multiply of :152-186 over NVLink peer memory: tiles are PULLED by the ranks that need them with
-        copy-engine DMA on a side stream (B tiles in column chunks, so the first GEMM chunk starts after A plus one
-        chunk has landed), and a non-owner partial of C is stored by the GEMM epilogue directly into a staging slot in
-        the owner's HBM; the owner adds it.  Returns None (on every rank) if some tile is a strided view."""
-        rank, ws = mesh.rank, mesh.ws
+        """The multiply of :152-186 on the C-ABI engine (`mb_matmul_blocked_dist`, csrc/dist.cu): mapping of the m*k*n
+        products to ranks, tile pulls over NVLink peer memory, the DMMA products and the reduce of the k partials all
+        happen behind the ABI; this method only describes who owns what and allocates the C tiles this rank will own."""
+        import ctypes as C
+        rank = mesh.rank
         m, k, n = plan.m, plan.k, plan.n
-        dir_a = self._peer_directory(mesh, a_local)
-        dir_b = other._peer_directory(mesh, b_local)
-        if dir_a is None or dir_b is None:
-            return None
         M, K, N = self.numRows(), self.numCols(), other.numCols()
         bm, bk, bn = _ceil_len(M, m), _ceil_len(K, k), _ceil_len(N, n)
-        dims_a = lambda i, kk: (min(bm, M - i * bm), min(bk, K - kk * bk))
-        dims_b = lambda kk, j: (min(bk, K - kk * bk), min(bn, N - j * bn))
+        row_len = (C.c_int32 * m)(*[min(bm, M - i * bm) for i in range(m)])
+        k_len = (C.c_int32 * k)(*[min(bk, K - kk * bk) for kk in range(k)])
+        col_len = (C.c_int32 * n)(*[min(bn, N - j * bn) for j in range(n)])
         tdt = self._global_dtype()
-        esz = torch.empty(0, dtype=tdt).element_size()
-        out_tdt = torch.float32 if tdt == torch.bfloat16 else tdt
-        osz = torch.empty(0, dtype=out_tdt).element_size()
+        if tdt not in (torch.float64, torch.bfloat16):
+            return None                                         # fp32 tiles: NCCL path (every rank takes the same branch)
+        dt = nat.MB_F64 if tdt == torch.float64 else nat.MB_BF16
+        out_dt = nat.MB_F64 if tdt == torch.float64 else nat.MB_F32
         rt = Runtime.get()
-        dev = rt.device
-        e = mesh.epoch = mesh.epoch + 1
-        S = torch.cuda.current_stream(dev)
-        X = mesh.copy_stream
-
-        # ---- staging slots on each owner for the partials it receives (same arithmetic on every rank) ----
-        slot: Dict[Tuple[int, int, Tuple[int, int]], int] = {}
-        need: Dict[int, int] = {}
-        for (src, dst, key) in plan.c_reduces:
-            r_, c_ = min(bm, M - key[0] * bm), min(bn, N - key[1] * bn)
-            off = need.get(dst, 0)
-            slot[(src, dst, key)] = off
-            need[dst] = off + ((r_ * c_ * osz + 255) // 256) * 256
-        if need:
-            mesh.ensure_staging(max(need.values()))
-
-        # ---- 1. tell the ranks that will pull from me that my tiles are ready (stream-ordered) ----
-        consumers = sorted({d for (s_, d, _) in plan.a_sends + plan.b_sends if s_ == rank})
-        for d in consumers:
-            mesh.signal(d, peer.CH_READY, e)
-
-        # ---- 2. pull the tiles I need, in first-use order, on the copy stream ----
-        mine = plan.products.get(rank, [])
-        pulls = []                                  # (kind, key, src)
-        for (i, j, kk) in mine:
-            if (i, kk) not in a_local and ("A", (i, kk)) not in [(p[0], p[1]) for p in pulls]:
-                pulls.append(("A", (i, kk), dir_a[(i, kk)][0]))
-            if (kk, j) not in b_local and ("B", (kk, j)) not in [(p[0], p[1]) for p in pulls]:
-                pulls.append(("B", (kk, j), dir_b[(kk, j)][0]))
-        a_tiles: Dict[Tuple[int, int], SubMatrix] = dict(a_local)
-        b_tiles: Dict[Tuple[int, int], SubMatrix] = dict(b_local)
-        events: Dict[Tuple[str, Tuple[int, int]], list] = {}
-        chunks_of: Dict[Tuple[int, int], list] = {}
-        bufs = {}
-        for kind, key, src in pulls:                # allocate on the compute stream's allocator pool
-            r_, c_ = dims_a(*key) if kind == "A" else dims_b(*key)
-            bufs[(kind, key)] = torch.empty(r_ * c_, dtype=tdt, device=dev)
-        if pulls:
-            X.wait_stream(S)
-            if True:
-                with torch.cuda.stream(X):
-                    waited = []
-                    for kind, key, src in pulls:
-                        if src not in waited:
-                            mesh.wait(peer.CH_READY, src, e)
-                            waited.append(src)
-                        r_, c_ = dims_a(*key) if kind == "A" else dims_b(*key)
-                        buf = bufs[(kind, key)]
-                        src_ptr = mesh.open((dir_a if kind == "A" else dir_b)[key][1])
-                        nbytes = r_ * c_ * esz
-                        nch = 4 if (kind == "B" and nbytes >= (32 << 20) and c_ >= 4) else 1
-                        bounds = [(c_ * q) // nch for q in range(nch + 1)]
-                        evs = []
-                        for q in range(nch):
-                            lo, hi = bounds[q] * r_ * esz, bounds[q + 1] * r_ * esz
-                            mesh.memcpy(buf.data_ptr() + lo, src_ptr + lo, hi - lo)
-                            ev = torch.cuda.Event()
-                            ev.record(X)
-                            evs.append(ev)
-                        events[(kind, key)] = evs
-                        if kind == "B":
-                            chunks_of[key] = bounds
-                        tile = SubMatrix(buf=buf, rows=r_, cols=c_, ld=max(1, r_))
-                        (a_tiles if kind == "A" else b_tiles)[key] = tile
-                    for src in waited:
-                        mesh.signal(src, peer.CH_DONE, e)
-            rt.sync_stream()
-
-        # ---- 3. my block products, seq order; a non-owner partial goes straight into the owner's staging slot ----
-        from .sub_matrix import RawBlock
-        by_c: Dict[Tuple[int, int], List[int]] = {}
-        for (i, j, kk) in mine:
-            by_c.setdefault((i, j), []).append(kk)
+        rt.sync_stream()
+        a_arr = (nat.c_blk * (m * k))()
+        b_arr = (nat.c_blk * (k * n))()
+        c_arr = (nat.c_blk * (m * n))()
+        a_own = (C.c_int32 * (m * k))(*[self.owner(i, kk) for i in range(m) for kk in range(k)])
+        b_own = (C.c_int32 * (k * n))(*[other.owner(kk, j) for kk in range(k) for j in range(n)])
+        for (i, kk), s in a_local.items():
+            a_arr[i * k + kk] = s.handle()
+        for (kk, j), s in b_local.items():
+            b_arr[kk * n + j] = s.handle()
+        _, c_owner = mesh.plan(m, k, n)
         partial: Dict[Tuple[int, int], SubMatrix] = {}
-        remote_out: Dict[Tuple[int, int], object] = {}
-        pushed_to = []
-        for (i, j), kks in by_c.items():
-            owner = plan.c_owner[(i, j)]
-            r_, c_ = min(bm, M - i * bm), min(bn, N - j * bn)
-            if owner != rank and len(kks) == 1:
-                prev = mesh.last_partial_epoch.get(owner, 0)
-                if prev and owner not in pushed_to:
-                    mesh.wait(peer.CH_FREE, owner, prev)         # the owner has consumed my previous partial
-                odt = nat.MB_F32 if tdt == torch.bfloat16 else (nat.MB_F64 if tdt == torch.float64 else nat.MB_F32)
-                remote_out[(i, j)] = RawBlock(mesh.staging_peer[owner] + slot[(rank, owner, (i, j))], r_, c_, max(1, r_), odt)
-                if owner not in pushed_to:
-                    pushed_to.append(owner)
-        for (i, j, kk) in mine:
-            a, b = a_tiles[(i, kk)], b_tiles[(kk, j)]
-            for ev in events.pop(("A", (i, kk)), []):
-                S.wait_event(ev)
-            evs_b = events.pop(("B", (kk, j)), [])
-            if (i, j) in remote_out:
-                out, acc = remote_out[(i, j)], False
-            else:
-                acc = (i, j) in partial
-                if not acc:
-                    odt = nat.MB_F32 if a.dtype == nat.MB_BF16 else a.dtype
-                    partial[(i, j)] = SubMatrix.empty(a.rows, b.cols, odt, dev)
-                out = partial[(i, j)]
-            with profiling.phase("gemm"):
-                if len(evs_b) > 1:
-                    bounds = chunks_of[(kk, j)]
-                    for q, ev in enumerate(evs_b):
-                        S.wait_event(ev)
-                        c0, c1 = bounds[q], bounds[q + 1]
-                        if c1 > c0:
-                            a.multiply(b.slice(0, b.rows, c0, c1), out=out.slice(0, out.rows, c0, c1), accumulate=acc)
-                else:
-                    for ev in evs_b:
-                        S.wait_event(ev)
-                    a.multiply(b, out=out, accumulate=acc)
-        # partials I hold for somebody else's C tile
-        for (src, dst, key) in plan.c_reduces:
-            if src != rank:
-                continue
-            if key not in remote_out:                        # several kk summed locally first: push the sum with one DMA
-                prev = mesh.last_partial_epoch.get(dst, 0)
-                if prev and dst not in pushed_to:
-                    mesh.wait(peer.CH_FREE, dst, prev)
-                p_ = partial.pop(key)
-                mesh.memcpy(mesh.staging_peer[dst] + slot[(src, dst, key)], p_.buf.data_ptr(), p_.rows * p_.cols * osz)
-                if dst not in pushed_to:
-                    pushed_to.append(dst)
-        for dst in pushed_to:
-            mesh.signal(dst, peer.CH_PARTIAL, e)
-            mesh.last_partial_epoch[dst] = e
-
-        # ---- 4. owner side: add the partials that were stored into my staging ----
-        with profiling.phase("reduce"):
-            srcs = []
-            for (src, dst, key) in plan.c_reduces:
-                if dst != rank:
-                    continue
-                if src not in srcs:
-                    mesh.wait(peer.CH_PARTIAL, src, e)
-                    srcs.append(src)
-                p_ = partial[key]
-                off = slot[(src, dst, key)]
-                view = mesh.staging[off:off + p_.rows * p_.cols * osz].view(out_tdt)
-                p_.add_(SubMatrix(buf=view, rows=p_.rows, cols=p_.cols, ld=max(1, p_.rows)))
-            for src in srcs:
-                mesh.signal(src, peer.CH_FREE, e)
-
-        # ---- 5. my tiles may not be overwritten / freed until everyone has finished pulling them ----
-        for d in consumers:
-            mesh.wait(peer.CH_DONE, d, e)
-
+        for i in range(m):
+            for j in range(n):
+                if c_owner[i * n + j] == rank:
+                    partial[(i, j)] = SubMatrix.empty(row_len[i], col_len[j], out_dt, rt.device)
+                    c_arr[i * n + j] = partial[(i, j)].handle()
+        with profiling.phase("gemm"):
+            nat.check(rt.lib.mb_matmul_blocked_dist(mesh.comm, a_arr, a_own, b_arr, b_own, m, k, n, row_len, k_len, col_len, dt, c_arr))
         result = [(BlockID(i, j), blk) for (i, j), blk in sorted(partial.items())]
-        owners = dict(plan.c_owner)
+        owners = {(i, j): c_owner[i * n + j] for i in range(m) for j in range(n)}
         return BlockMatrix(result, M, N, m, n, placement=lambda r, c, o=owners: o[(r, c)])
 
     def _local_dtype(self):

@@ -1,0 +1,115 @@
+"""One rank of the torch-free multi-process test of the C-ABI multi-GPU multiply (mb_comm_* / mb_matmul_blocked_dist).
+Only ctypes + numpy + the CPU oracle: no torch, no NCCL.   argv: rank world session [devices]
+Ranks map to device rank % devices, so the protocol (shared-memory rendezvous, CUDA IPC pulls, band flags, fused
+reduce-scatter, staged adds, FREE/DONE handshakes) is exercised on a one-GPU box too (two processes time-slicing it)."""
+import ctypes as C
+import os
+import sys
+from pathlib import Path
+
+import numpy as np
+
+sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
+from marlin_b200 import _native as nat          # noqa: E402  (ctypes declarations only)
+from oracle import reference_model as rm        # noqa: E402
+
+
+def main():
+    rank, world, session = int(sys.argv[1]), int(sys.argv[2]), sys.argv[3]
+    ndev = int(sys.argv[4]) if len(sys.argv) > 4 else world
+    lib = nat.load(build_if_missing=False)
+    ctx = nat.c_ctx()
+    nat.check(lib.mb_init(rank % ndev, C.byref(ctx)))
+    comm = C.c_void_p()
+    nat.check(lib.mb_comm_init(ctx, rank, world, session.encode(), C.byref(comm)))
+    assert lib.mb_comm_rank(comm) == rank and lib.mb_comm_world(comm) == world
+
+    def upload(mat, view=None):
+        """A device block holding `mat`; view = 'T' stores the transpose and hands out a transposed view, 'pad' a
+        slice of a taller allocation (odd leading dimension handling is the library's business)."""
+        f = np.asfortranarray(mat, dtype=np.float64)
+        h = nat.c_blk()
+        if view == "T":
+            ft = np.asfortranarray(f.T)
+            nat.check(lib.mb_block_upload(ctx, ft.ctypes.data_as(C.c_void_p), 0, ft.shape[0], ft.shape[1], max(1, ft.shape[0]), 0,
+                                          nat.MB_F64, C.byref(h)))
+            v = nat.c_blk()
+            nat.check(lib.mb_block_view_t(ctx, h, C.byref(v)))
+            return v
+        if view == "pad":
+            big = nat.c_blk()
+            nat.check(lib.mb_block_alloc(ctx, f.shape[0] + 3, f.shape[1], nat.MB_F64, C.byref(big)))
+            v = nat.c_blk()
+            nat.check(lib.mb_block_slice(ctx, big, 1, 1 + f.shape[0], 0, f.shape[1], C.byref(v)))
+            nat.check(lib.mb_block_upload(ctx, f.ctypes.data_as(C.c_void_p), 0, f.shape[0], f.shape[1], max(1, f.shape[0]), 0,
+                                          nat.MB_F64, C.byref(h)))
+            nat.check(lib.mb_block_copy(ctx, h, v))
+            return v
+        nat.check(lib.mb_block_upload(ctx, f.ctypes.data_as(C.c_void_p), 0, f.shape[0], f.shape[1], max(1, f.shape[0]), 0, nat.MB_F64,
+                                      C.byref(h)))
+        return h
+
+    rng = np.random.default_rng(2026)               # the same stream on every rank
+    # alternating plans: fused pairs, staged reduces with different slot layouts (the round-1 staging race: a (2,2,2)
+    # multiply followed by a (1,8,1) one), C-stationary plans, ragged blocks, views; `place` shifts the owner maps.
+    cases = [(256, 384, 640, 2, 2, 2, 0, None), (96, 1024, 64, 1, 8, 1, 1, None), (300, 260, 212, 2, 2, 2, 3, None),
+             (1300, 520, 1400, 1, 2, 1, 0, None), (130, 120, 110, 3, 2, 2, 2, None), (256, 256, 256, 4, 4, 4, 1, None),
+             (200, 300, 160, 2, 3, 1, 0, "T"), (1300, 520, 1400, 1, 2, 1, 1, None), (260, 520, 300, 1, 2, 2, 5, "pad"),
+             (64, 512, 64, 1, 8, 1, 0, None), (1100, 260, 1200, 2, 1, 2, 1, None)]
+    worst = 0.0
+    for rep in range(2):
+        for (M, K, N, m, k, n, place, view) in cases:
+            A, B = rng.random((M, K)) - 0.5, rng.random((K, N)) - 0.5
+            oa = rm.DenseVecMatrix(list(enumerate(A))).to_block_matrix(m, k)
+            ob = rm.DenseVecMatrix(list(enumerate(B))).to_block_matrix(k, n)
+            ta, tb = dict(oa.blocks), dict(ob.blocks)
+            ref = dict(oa.multiply(ob, gemm="blas").blocks)
+            a_own = [(i * k + kk + place) % world for i in range(m) for kk in range(k)]
+            b_own = [(kk * n + j + 2 * place) % world for kk in range(k) for j in range(n)]
+            a_h = (nat.c_blk * (m * k))()
+            b_h = (nat.c_blk * (k * n))()
+            c_h = (nat.c_blk * (m * n))()
+            for t in range(m * k):
+                if a_own[t] == rank:
+                    a_h[t] = upload(ta[(t // k, t % k)], view if t % 2 == 0 else None)
+            for t in range(k * n):
+                if b_own[t] == rank:
+                    b_h[t] = upload(tb[(t // n, t % n)], view if t % 2 == 1 else None)
+            pr = (C.c_int32 * (m * k * n))()
+            co = (C.c_int32 * (m * n))()
+            nat.check(lib.mb_dist_plan(m, k, n, world, pr, co))
+            row_len = (C.c_int32 * m)(*[ta[(i, 0)].shape[0] for i in range(m)])
+            k_len = (C.c_int32 * k)(*[ta[(0, kk)].shape[1] for kk in range(k)])
+            col_len = (C.c_int32 * n)(*[tb[(0, j)].shape[1] for j in range(n)])
+            mine = [t for t in range(m * n) if co[t] == rank]
+            for t in mine:
+                h = nat.c_blk()
+                nat.check(lib.mb_block_alloc(ctx, row_len[t // n], col_len[t % n], nat.MB_F64, C.byref(h)))
+                nat.check(lib.mb_block_fill(ctx, h, float("nan")))
+                c_h[t] = h
+            for _ in range(2):                                   # back-to-back epochs reuse staging slots and flags
+                nat.check(lib.mb_matmul_blocked_dist(comm, a_h, (C.c_int32 * (m * k))(*a_own), b_h, (C.c_int32 * (k * n))(*b_own),
+                                                     m, k, n, row_len, k_len, col_len, nat.MB_F64, c_h))
+            for t in mine:
+                i, j = divmod(t, n)
+                got = np.empty((row_len[i], col_len[j]), order="F")
+                nat.check(lib.mb_block_download(ctx, c_h[t], got.ctypes.data_as(C.c_void_p), max(1, row_len[i])))
+                Ai = np.hstack([ta[(i, kk)] for kk in range(k)])
+                Bj = np.vstack([tb[(kk, j)] for kk in range(k)])
+                err = (np.abs(got - ref[(i, j)]) / (np.abs(Ai) @ np.abs(Bj))).max()
+                assert err <= 1e-10, (rep, M, K, N, m, k, n, place, view, i, j, err)
+                worst = max(worst, err)
+            nat.check(lib.mb_comm_check(comm))
+            for arr in (a_h, b_h, c_h):
+                for h in arr:
+                    if h:
+                        nat.check(lib.mb_block_free(ctx, h))
+    nat.check(lib.mb_comm_barrier(comm))
+    nat.check(lib.mb_comm_destroy(comm))
+    nat.check(lib.mb_shutdown(ctx))
+    assert "torch" not in sys.modules, "this worker must stay torch-free"
+    print(f"cabi rank {rank}/{world} ok worst_scaled_err={worst:.2e} slow={os.environ.get('MARLIN_B200_DIST_SLOW', '0')}", flush=True)
+
+
+if __name__ == "__main__":
+    main()

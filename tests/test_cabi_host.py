@@ -140,3 +140,22 @@ def test_plan_multiply_cfg3_and_cfg5():
     p5 = comm.plan_multiply(4, 4, 4, 8, lambda r, c: comm.elem_owner(r, c, 4, 8), lambda r, c: comm.elem_owner(r, c, 4, 8))
     assert p5.c_reduces == [] and all(len(v) == 8 for v in p5.products.values())
     assert {(i, j) for (i, j, kk) in p5.products[3]} == {(1, 2), (1, 3)}
+
+
+def test_dist_plan_matches_python_plan():
+    """mb_dist_plan (csrc/dist.cu) and comm.plan_multiply deal the m*k*n products (seq = i*n*k + j*k + kk,
+    BlockMatrix.scala:163,168) to ranks identically, and agree on the owner of every C tile."""
+    import ctypes as C
+    from marlin_b200 import comm
+    lib = nat.load()
+    for (m, k, n) in [(2, 2, 2), (1, 8, 1), (4, 4, 4), (3, 2, 2), (2, 3, 1), (1, 1, 1), (5, 1, 3)]:
+        for world in (1, 2, 3, 4, 8):
+            pr = (C.c_int32 * (m * k * n))()
+            co = (C.c_int32 * (m * n))()
+            assert lib.mb_dist_plan(m, k, n, world, pr, co) == 0
+            plan = comm.plan_multiply(m, k, n, world, lambda r, c: 0, lambda r, c: 0)
+            for r, prods in plan.products.items():
+                for (i, j, kk) in prods:
+                    assert pr[i * n * k + j * k + kk] == r
+            for (i, j), o in plan.c_owner.items():
+                assert co[i * n + j] == o

@@ -1,0 +1,48 @@
+"""The multi-GPU multiply through the C ABI alone (mb_comm_init / mb_matmul_blocked_dist): N processes, ctypes + numpy,
+no torch and no NCCL anywhere (tests/dist_cabi_worker.py).  With fewer GPUs than ranks the ranks share devices, so the
+whole protocol also runs on a one-GPU box."""
+import os
+import subprocess
+import sys
+import uuid
+from pathlib import Path
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = Path(__file__).resolve().parents[1]
+
+
+def _run(world, ndev, slow, timeout=900):
+    session = uuid.uuid4().hex[:16]
+    env = dict(os.environ, MARLIN_B200_TIMEOUT_S="90", MARLIN_B200_DIST_SLOW="1" if slow else "0")
+    procs = [subprocess.Popen([sys.executable, str(ROOT / "tests" / "dist_cabi_worker.py"), str(r), str(world), session, str(ndev)],
+                              stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env) for r in range(world)]
+    outs = []
+    for p in procs:
+        try:
+            out, _ = p.communicate(timeout=timeout)
+        except subprocess.TimeoutExpired:
+            for q in procs:
+                q.kill()
+            raise
+        outs.append((p.returncode, out))
+    for r, (rc, out) in enumerate(outs):
+        assert rc == 0 and f"cabi rank {r}/{world} ok" in out, f"rank {r}:\n{out[-3000:]}"
+
+
+@pytest.mark.parametrize("slow", [False, True])
+def test_dist_multiply_cabi_two_ranks(slow):
+    """fast = one grouped DMMA launch per rank with band flags + the fused reduce-scatter; slow = staged partials and
+    per-tile launches (the path bf16 / transposed tiles take), forced here for fp64 so both are checked bit-for-tolerance."""
+    import torch
+    ndev = torch.cuda.device_count()
+    _run(2, min(2, ndev), slow)
+
+
+def test_dist_multiply_cabi_all_gpus():
+    import torch
+    ndev = torch.cuda.device_count()
+    if ndev < 3:
+        pytest.skip("needs >= 3 GPUs (the 2-rank case runs everywhere)")
+    _run(min(ndev, 8), min(ndev, 8), False)
