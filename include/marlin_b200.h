@@ -256,6 +256,22 @@ int32_t mb_matmul_blocked_dist(mb_comm* comm, mb_block* const* A_tiles, const in
                                const int32_t* row_len, const int32_t* k_len, const int32_t* col_len, int32_t dtype,
                                mb_block* const* C_tiles);
 
+/* The same multiply END TO END with HOST tiles (what bench.py reports as e2e at N > 1): every input tile is uploaded by
+ * ONE of the ranks that need it (a_home / b_home; mb_dist_host_homes spreads them over the PCIe links) and pulled over
+ * NVLink by the others, band by band; one grouped DMMA launch per rank starts on the first bands; the two holders of a
+ * k-split C tile each reduce and download a checkerboard of its sub-blocks, hidden behind the rest of the GEMM.
+ * A_host / B_host: packed column-major tiles, non-NULL where homed; C_host[i*n+j]: the packed host tile, non-NULL on
+ * every rank that computes a partial of it (use one mb_host_alloc_shared array per tile so that the ranks fill one copy).
+ * fp64, at most two holders per C tile.  Blocking. */
+int32_t mb_dist_host_homes(int32_t m, int32_t k, int32_t n, int32_t world, int32_t* a_home, int32_t* b_home);
+int32_t mb_matmul_blocked_dist_host(mb_comm* comm, const double* const* A_host, const int32_t* a_home,
+                                    const double* const* B_host, const int32_t* b_home, int32_t m, int32_t k, int32_t n,
+                                    const int32_t* row_len, const int32_t* k_len, const int32_t* col_len,
+                                    double* const* C_host);
+/* Pinned host memory shared by the processes of one box (POSIX shm `name` + cudaHostRegister). */
+int32_t mb_host_alloc_shared(const char* name, int64_t bytes, void** out);
+int32_t mb_host_free_shared(const char* name, void* ptr, int64_t bytes, int32_t unlink_name);
+
 /* ---- rows <-> blocks on device (matrix/DenseVecMatrix.scala:1084-1223, 1259-1328;
  *      matrix/BlockMatrix.scala:575-594): a DenseVecMatrix shard is a row-major (rows x cols)
  *      buffer, i.e. a transposed block; these are strided copies (mb_block_copy on views). */

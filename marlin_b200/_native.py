@@ -101,6 +101,11 @@ SIGNATURES = {
     "mb_comm_barrier": (c_i32, [C.c_void_p]),
     "mb_comm_check": (c_i32, [C.c_void_p]),
     "mb_dist_plan": (c_i32, [c_i32, c_i32, c_i32, c_i32, C.POINTER(c_i32), C.POINTER(c_i32)]),
+    "mb_dist_host_homes": (c_i32, [c_i32, c_i32, c_i32, c_i32, C.POINTER(c_i32), C.POINTER(c_i32)]),
+    "mb_matmul_blocked_dist_host": (c_i32, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(c_i32), C.POINTER(C.c_void_p), C.POINTER(c_i32),
+                                            c_i32, c_i32, c_i32, C.POINTER(c_i32), C.POINTER(c_i32), C.POINTER(c_i32), C.POINTER(C.c_void_p)]),
+    "mb_host_alloc_shared": (c_i32, [C.c_char_p, c_i64, C.POINTER(C.c_void_p)]),
+    "mb_host_free_shared": (c_i32, [C.c_char_p, C.c_void_p, c_i64, c_i32]),
     "mb_matmul_blocked_dist": (c_i32, [C.c_void_p, C.POINTER(c_blk), C.POINTER(c_i32), C.POINTER(c_blk), C.POINTER(c_i32), c_i32, c_i32,
                                        c_i32, C.POINTER(c_i32), C.POINTER(c_i32), C.POINTER(c_i32), c_i32, C.POINTER(c_blk)]),
 }

@@ -48,8 +48,9 @@ constexpr int F_PART2 = 64;                           // [src][slot]            
 constexpr int F_FINAL2 = F_PART2 + MAXW * MAX_PAIR;   // [src][slot]               (fused: partner's reduced half is in my C tile)
 constexpr int F_UPREADY = F_FINAL2 + MAXW * MAX_PAIR; // [src][tile slot][band]    host path: a band of src's uploaded tile is in its HBM
 constexpr int UP_SLOTS = 8;
-constexpr int F_SUBPART = F_UPREADY + MAXW * UP_SLOTS * MAX_BANDS;   // [src]: count of sub-blocks src has stored into my staging (host path)
-constexpr int F_LOCAL = F_SUBPART + MAXW;             // ---- local from here ----
+constexpr int SUB_SLOTS = 64;                         // host path: sub-blocks per (src -> me) pair and call
+constexpr int F_SUBDONE = F_UPREADY + MAXW * UP_SLOTS * MAX_BANDS;   // [src][sub-block]   host path: src's partial of the sub-block is in my staging
+constexpr int F_LOCAL = F_SUBDONE + MAXW * SUB_SLOTS;             // ---- local from here ----
 constexpr int F_BAND = F_LOCAL;                       // [operand tile][band]      2 * G2_MAX_OPS * MAX_BANDS
 constexpr int F_CTR = F_BAND + 2 * mb::G2_MAX_OPS * MAX_BANDS;       // done counters, one per entry
 constexpr int F_SIG = F_CTR + mb::G2_MAX_ENTRIES;                    // local completion flags, one per entry
@@ -223,7 +224,7 @@ int32_t ensure_staging(mb_comm* c, size_t need_slot) {
         ShmRank& o = c->shm->r[p];
         if (o.staging_seq.load(std::memory_order_acquire) != gen) return fail(MB_ERR_INVALID_ARG, "mb_comm: staging generations differ across ranks");
         void* base = nullptr;
-        MB_CUDA(mb::ipc_open(o.staging_handle, &base));
+        MB_CUDA(mb::ipc_open_ex(o.staging_handle, &base, true));
         c->staging_peer[p] = static_cast<char*>(base) + o.staging_off;
     }
     for (int p = 0; p < c->world; ++p) c->last_write_epoch[p] = 0;
@@ -343,7 +344,7 @@ int32_t mb_comm_init(mb_ctx* ctx, int32_t rank, int32_t world, const char* sessi
         if (r) return bail(r);
         if (q == rank) { c->flags_peer[q] = c->flags; continue; }
         void* base = nullptr;
-        e = mb::ipc_open(c->shm->r[q].flags_handle, &base);
+        e = mb::ipc_open_ex(c->shm->r[q].flags_handle, &base, true);
         if (e != cudaSuccess) return bail(cuda_fail(e, "mb_comm_init: cudaIpcOpenMemHandle (peer access between the GPUs?)"));
         c->flags_peer[q] = reinterpret_cast<unsigned long long*>(static_cast<char*>(base) + c->shm->r[q].flags_off);
     }
@@ -463,6 +464,19 @@ int32_t mb_matmul_blocked_dist(mb_comm* c, mb_block* const* A_tiles, const int32
         }
     for (int t = 0; t < m * k; ++t) if (!entA[t]) return fail(MB_ERR_INVALID_ARG, "mb_matmul_blocked_dist: rank %d did not publish A tile %d", a_owner[t], t);
     for (int t = 0; t < k * n; ++t) if (!entB[t]) return fail(MB_ERR_INVALID_ARG, "mb_matmul_blocked_dist: rank %d did not publish B tile %d", b_owner[t], t);
+
+    // Map every peer allocation this call will touch BEFORE any pointer is taken: opening a handle can evict stale
+    // mappings (see ipc_open_ex), which would invalidate pointers handed out earlier in the same call.  A second pass
+    // after an eviction only hits the cache.
+    for (int attempt = 0; attempt < 3; ++attempt) {
+        const unsigned long long gen = mb::ipc_evictions();
+        char* dummy = nullptr;
+        for (int p = 0; p < world; ++p)
+            if (p != rank)
+                for (const ShmEntry& en : dir[p])
+                    if ((rc = open_entry(en, &dummy)) != MB_OK) return rc;
+        if (mb::ipc_evictions() == gen) break;
+    }
 
     // ---- the same decision on every rank: can the whole call use the grouped DMMA launch / the fused reduce-scatter? ----
     bool fast = dtype == MB_F64 && k <= mb::G2_MAX_SEG;
@@ -825,6 +839,417 @@ int32_t mb_matmul_blocked_dist(mb_comm* c, mb_block* const* A_tiles, const int32
         return fail(MB_ERR_TIMEOUT, "mb_matmul_blocked_dist: a device-side wait for a peer timed out in an earlier call");
     MB_CUDA(cudaMemcpyAsync(c->status_host, c->flags + F_STATUS, 8, cudaMemcpyDeviceToHost, S));
     (void)esz;
+    return MB_OK;
+}
+
+
+// ------------------------------------------------------------------------------------------------------------------
+// Placement of HOST tiles for the end-to-end path: every input tile is uploaded (H2D) by exactly one of the ranks that
+// need it, with the uploads spread as evenly as possible over the ranks' PCIe links; the other ranks that need the
+// tile pull it over NVLink.  Deterministic: smallest feasible per-rank tile count, found by bipartite matching.
+// ------------------------------------------------------------------------------------------------------------------
+int32_t mb_dist_host_homes(int32_t m, int32_t k, int32_t n, int32_t world, int32_t* a_home, int32_t* b_home) {
+    if (m <= 0 || k <= 0 || n <= 0 || world <= 0 || world > MAXW || !a_home || !b_home) return fail(MB_ERR_INVALID_ARG, "mb_dist_host_homes: bad argument");
+    const Plan plan = make_plan(m, k, n, world);
+    const int T = m * k + k * n;
+    std::vector<std::vector<int>> cand(T);
+    for (int i = 0; i < m; ++i)
+        for (int j = 0; j < n; ++j)
+            for (int kk = 0; kk < k; ++kk) {
+                const int r = plan.prod_rank[i * n * k + j * k + kk];
+                auto add = [&](int t) { if (std::find(cand[t].begin(), cand[t].end(), r) == cand[t].end()) cand[t].push_back(r); };
+                add(i * k + kk);
+                add(m * k + kk * n + j);
+            }
+    for (auto& cnd : cand) std::sort(cnd.begin(), cnd.end());
+    for (int cap = (T + world - 1) / world; cap <= T; ++cap) {
+        std::vector<std::vector<int>> held(world);              // rank -> tiles assigned
+        std::vector<int> home(T, -1);
+        // Kuhn's augmenting paths with rank capacity `cap`
+        std::vector<char> seen;
+        struct Rec { static bool go(int t, int cap, std::vector<std::vector<int>>& cand, std::vector<std::vector<int>>& held,
+                                    std::vector<int>& home, std::vector<char>& seen) {
+            for (int r : cand[t]) {
+                if (seen[r]) continue;
+                seen[r] = 1;
+                if ((int)held[r].size() < cap) { held[r].push_back(t); home[t] = r; return true; }
+                for (size_t x = 0; x < held[r].size(); ++x) {
+                    const int other = held[r][x];
+                    if (go(other, cap, cand, held, home, seen)) { held[r][x] = t; home[t] = r; return true; }
+                }
+            }
+            return false;
+        } };
+        bool ok = true;
+        for (int t = 0; t < T && ok; ++t) {
+            seen.assign(world, 0);
+            ok = Rec::go(t, cap, cand, held, home, seen);
+        }
+        if (ok) {
+            for (int t = 0; t < m * k; ++t) a_home[t] = home[t];
+            for (int t = 0; t < k * n; ++t) b_home[t] = home[m * k + t];
+            return MB_OK;
+        }
+    }
+    return fail(MB_ERR_UNSUPPORTED, "mb_dist_host_homes: no assignment");
+}
+
+// Pinned host memory shared by the ranks of one box (POSIX shm + cudaHostRegister): lets the ranks that reduce
+// different parts of one C tile write them into ONE host array, and lets a test read the whole result in one process.
+int32_t mb_host_alloc_shared(const char* name, int64_t bytes, void** out) {
+    if (!name || bytes <= 0 || !out) return fail(MB_ERR_INVALID_ARG, "mb_host_alloc_shared: bad argument");
+    std::string nm = std::string("/marlin_b200_h_") + name;
+    const int fd = shm_open(nm.c_str(), O_CREAT | O_RDWR, 0600);
+    if (fd < 0) return fail(MB_ERR_OOM, "mb_host_alloc_shared: shm_open(%s) failed", nm.c_str());
+    if (ftruncate(fd, (off_t)bytes) != 0) { close(fd); return fail(MB_ERR_OOM, "mb_host_alloc_shared: ftruncate(%lld) failed", (long long)bytes); }
+    void* p = mmap(nullptr, (size_t)bytes, PROT_READ | PROT_WRITE, MAP_SHARED | MAP_POPULATE, fd, 0);
+    close(fd);
+    if (p == MAP_FAILED) return fail(MB_ERR_OOM, "mb_host_alloc_shared: mmap failed");
+    cudaError_t e = cudaHostRegister(p, (size_t)bytes, cudaHostRegisterPortable);
+    if (e != cudaSuccess) { munmap(p, (size_t)bytes); return cuda_fail(e, "cudaHostRegister"); }
+    *out = p;
+    return MB_OK;
+}
+int32_t mb_host_free_shared(const char* name, void* ptr, int64_t bytes, int32_t unlink_name) {
+    if (ptr) { cudaHostUnregister(ptr); munmap(ptr, (size_t)bytes); }
+    if (unlink_name && name) shm_unlink((std::string("/marlin_b200_h_") + name).c_str());
+    return MB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// The same multiply END TO END: HOST tiles in, HOST tiles out, across the ranks of `comm` (bench.py's e2e at N > 1).
+// A_host[i*k+kk] / B_host[kk*n+j]: packed column-major fp64 host tiles, non-NULL on the rank a_home / b_home names
+// (mb_dist_host_homes spreads them over the PCIe links); C_host[i*n+j]: the packed (row_len[i] x col_len[j]) host tile,
+// non-NULL on every rank that computes a partial of it (mb_dist_plan).  The two holders of a k-split tile each
+// reduce and download a checkerboard of its (row band x column band) sub-blocks, so with one shared host array per tile
+// (mb_host_alloc_shared) the tile is complete when every rank has returned.
+//   upload stream   : my tiles, band by band (A: row bands, B: column bands), each band announced to its consumers;
+//   pull stream     : the other tiles I need, band by band over NVLink as their uploaders announce them;
+//   compute stream  : ONE grouped DMMA launch over the sub-blocks in wavefront order (sub-block (p,q) needs band p of
+//                     the A tiles and band q of the B tiles); its producer waits per band, so the tensor cores start
+//                     after a quarter of each tile has crossed PCIe; sub-blocks the peer reduces are stored by the
+//                     epilogue straight into the peer's staging buffer;
+//   reduce stream   : per finished sub-block: add the peer's staged partial, D2H — hidden behind the rest of the GEMM.
+// Blocking: returns when this rank's part of C is in host memory.
+// ------------------------------------------------------------------------------------------------------------------
+int32_t mb_matmul_blocked_dist_host(mb_comm* c, const double* const* A_host, const int32_t* a_home, const double* const* B_host,
+                                    const int32_t* b_home, int32_t m, int32_t k, int32_t n, const int32_t* row_len,
+                                    const int32_t* k_len, const int32_t* col_len, double* const* C_host) {
+    if (!c) return fail(MB_ERR_INVALID_ARG, "null communicator");
+    mb_ctx* ctx = c->ctx;
+    MB_CTX(ctx);
+    MB_LOCK(ctx);
+    if (!A_host || !B_host || !C_host || !a_home || !b_home || !row_len || !k_len || !col_len || m <= 0 || k <= 0 || n <= 0)
+        return fail(MB_ERR_INVALID_ARG, "mb_matmul_blocked_dist_host: bad argument");
+    const int rank = c->rank, world = c->world;
+    if (k > mb::G2_MAX_SEG) return fail(MB_ERR_UNSUPPORTED, "mb_matmul_blocked_dist_host: k = %d > %d", k, mb::G2_MAX_SEG);
+    for (int i = 0; i < m; ++i) if (row_len[i] <= 0) return fail(MB_ERR_UNSUPPORTED, "mb_matmul_blocked_dist_host: empty block row");
+    for (int kk = 0; kk < k; ++kk) if (k_len[kk] <= 0) return fail(MB_ERR_UNSUPPORTED, "mb_matmul_blocked_dist_host: empty k segment");
+    for (int j = 0; j < n; ++j) if (col_len[j] <= 0) return fail(MB_ERR_UNSUPPORTED, "mb_matmul_blocked_dist_host: empty block column");
+    if (!ctx->h2d_stream) {
+        MB_CUDA(cudaStreamCreateWithFlags(&ctx->h2d_stream, cudaStreamNonBlocking));
+        MB_CUDA(cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking));
+    }
+    cudaStream_t S = ctx->stream, X = c->X, U = ctx->h2d_stream, R = c->R;
+    const Plan plan = make_plan(m, k, n, world);
+    // ---- global feasibility (the same verdict on every rank) ----
+    std::vector<int> ups(world, 0);
+    for (int t = 0; t < m * k; ++t) { if (a_home[t] < 0 || a_home[t] >= world) return fail(MB_ERR_INVALID_ARG, "bad a_home"); ++ups[a_home[t]]; }
+    for (int t = 0; t < k * n; ++t) { if (b_home[t] < 0 || b_home[t] >= world) return fail(MB_ERR_INVALID_ARG, "bad b_home"); ++ups[b_home[t]]; }
+    for (int r = 0; r < world; ++r) if (ups[r] > UP_SLOTS) return fail(MB_ERR_UNSUPPORTED, "mb_matmul_blocked_dist_host: rank %d would upload %d tiles (limit %d)", r, ups[r], UP_SLOTS);
+    for (int id = 0; id < m * n; ++id) if (plan.holders[id].size() > 2) return fail(MB_ERR_UNSUPPORTED, "mb_matmul_blocked_dist_host: C tile %d has %d holders (limit 2)", id, (int)plan.holders[id].size());
+    auto bands_of = [](int extent, int& band, int& nb) {
+        nb = extent >= 1024 ? MAX_BANDS : 1;
+        band = ((extent + nb - 1) / nb + 127) / 128 * 128;
+        nb = (extent + band - 1) / band;
+    };
+    for (int r = 0; r < world; ++r) {
+        std::vector<char> ua(m * k, 0), ub(k * n, 0);
+        int na = 0, nb = 0, subs = 0;
+        std::map<int, int> pair_subs;
+        for (int i = 0; i < m; ++i)
+            for (int j = 0; j < n; ++j) {
+                bool mine_ = false;
+                for (int kk = 0; kk < k; ++kk)
+                    if (plan.prod_rank[i * n * k + j * k + kk] == r) {
+                        mine_ = true;
+                        if (!ua[i * k + kk]) { ua[i * k + kk] = 1; ++na; }
+                        if (!ub[kk * n + j]) { ub[kk * n + j] = 1; ++nb; }
+                    }
+                if (mine_) {
+                    int ba, nba, bb, nbb;
+                    bands_of(row_len[i], ba, nba); bands_of(col_len[j], bb, nbb);
+                    subs += nba * nbb;
+                    const auto& h = plan.holders[i * n + j];
+                    if (h.size() == 2) pair_subs[h[0] == r ? h[1] : h[0]] += nba * nbb;
+                }
+            }
+        if (na > mb::G2_MAX_OPS || nb > mb::G2_MAX_OPS || subs > mb::G2_MAX_ENTRIES)
+            return fail(MB_ERR_UNSUPPORTED, "mb_matmul_blocked_dist_host: rank %d's share (%d sub-blocks) does not fit one grouped launch", r, subs);
+        for (auto& kv : pair_subs) if (kv.second > SUB_SLOTS) return fail(MB_ERR_UNSUPPORTED, "mb_matmul_blocked_dist_host: too many shared sub-blocks");
+    }
+    // ---- local checks ----
+    for (int t = 0; t < m * k; ++t) if (a_home[t] == rank && !A_host[t]) return fail(MB_ERR_INVALID_ARG, "mb_matmul_blocked_dist_host: A tile %d is homed here but NULL", t);
+    for (int t = 0; t < k * n; ++t) if (b_home[t] == rank && !B_host[t]) return fail(MB_ERR_INVALID_ARG, "mb_matmul_blocked_dist_host: B tile %d is homed here but NULL", t);
+    struct MyC { int id, i, j; std::vector<int> kks; };
+    std::vector<MyC> myc;
+    for (int i = 0; i < m; ++i)
+        for (int j = 0; j < n; ++j) {
+            MyC mc{i * n + j, i, j, {}};
+            for (int kk = 0; kk < k; ++kk) if (plan.prod_rank[i * n * k + j * k + kk] == rank) mc.kks.push_back(kk);
+            if (!mc.kks.empty()) {
+                if (!C_host[mc.id]) return fail(MB_ERR_INVALID_ARG, "mb_matmul_blocked_dist_host: C tile %d is computed here but NULL", mc.id);
+                myc.push_back(mc);
+            }
+        }
+    const unsigned long long e = ++c->epoch;
+    c->events_used = 0;
+    int32_t rc = MB_OK;
+
+    // ---- device layout in the arena: tiles I upload, tiles I pull, my C tiles ----
+    struct HTile { size_t off = 0; int rows = 0, cols = 0, ld = 0, home = -1, band = 0, nbands = 1, slot = -1, ready_base = -1, op = -1; bool need = false; char* peer = nullptr; };
+    std::vector<HTile> tA(m * k), tB(k * n);
+    size_t total = 0;
+    int nflag = 0;
+    std::vector<int> slot_ctr(world, 0);
+    for (int t = 0; t < m * k; ++t) { tA[t].rows = row_len[t / k]; tA[t].cols = k_len[t % k]; tA[t].home = a_home[t]; tA[t].slot = slot_ctr[a_home[t]]++; }
+    for (int t = 0; t < k * n; ++t) { tB[t].rows = k_len[t / n]; tB[t].cols = col_len[t % n]; tB[t].home = b_home[t]; tB[t].slot = slot_ctr[b_home[t]]++; }
+    for (const MyC& mc : myc)
+        for (int kk : mc.kks) { tA[mc.i * k + kk].need = true; tB[kk * n + mc.j].need = true; }
+    auto place = [&](HTile& t, bool is_a) {
+        t.ld = std::max(2, even(t.rows));
+        bands_of(is_a ? t.rows : t.cols, t.band, t.nbands);
+        if (t.home == rank || t.need) { t.off = total; total += up256((size_t)t.ld * t.cols * 8); }
+        if (t.need) { t.ready_base = nflag * MAX_BANDS; ++nflag; }
+    };
+    for (auto& t : tA) place(t, true);
+    for (auto& t : tB) place(t, false);
+    std::vector<size_t> coff(m * n, 0);
+    for (const MyC& mc : myc) { coff[mc.id] = total; total += up256((size_t)even(row_len[mc.i]) * col_len[mc.j] * 8); }
+    // The arena may be regrown (device sync inside): peers cannot still be pulling from the old one, because every call
+    // orders the DONE flags of its consumers on S before it ends.
+    if ((rc = ensure_arena(c, total)) != MB_OK) return rc;
+
+    // ---- staging: the partner's partial of a whole tile footprint per shared C tile ----
+    std::vector<size_t> slot_off(m * n, 0);
+    size_t need_slot = 0;
+    std::vector<int> pair_base(m * n, 0);                     // first F_SUBDONE index of the tile for its pair
+    {
+        std::map<std::pair<int, int>, size_t> used;
+        std::map<std::pair<int, int>, int> subs;
+        for (int id = 0; id < m * n; ++id) {
+            const auto& h = plan.holders[id];
+            if (h.size() != 2) continue;
+            const std::pair<int, int> key{std::min(h[0], h[1]), std::max(h[0], h[1])};
+            slot_off[id] = used[key];
+            used[key] += up256((size_t)even(row_len[id / n]) * col_len[id % n] * 8);
+            int ba, nba, bb, nbb;
+            bands_of(row_len[id / n], ba, nba); bands_of(col_len[id % n], bb, nbb);
+            pair_base[id] = subs[key];
+            subs[key] += nba * nbb;
+        }
+        for (auto& kv : used) need_slot = std::max(need_slot, kv.second);
+    }
+    if ((rc = ensure_staging(c, need_slot)) != MB_OK) return rc;
+
+    // ---- publish my upload buffers, read everybody's ----
+    std::vector<ShmEntry> mine;
+    auto pub = [&](const HTile& t, int kind, int idx) {
+        mb_block b;
+        b.data = c->arena + t.off; b.rows = t.rows; b.cols = t.cols; b.ld = t.ld; b.dtype = MB_F64;
+        ShmEntry en;
+        int32_t r = export_block(&b, kind, idx, &en);
+        if (r == MB_OK) mine.push_back(en);
+        return r;
+    };
+    for (int t = 0; t < m * k; ++t) if (tA[t].home == rank && (rc = pub(tA[t], 0, t)) != MB_OK) return rc;
+    for (int t = 0; t < k * n; ++t) if (tB[t].home == rank && (rc = pub(tB[t], 1, t)) != MB_OK) return rc;
+    if ((rc = publish(c, e, mine)) != MB_OK) return rc;
+    std::vector<std::vector<ShmEntry>> dir;
+    if ((rc = read_all(c, e, dir)) != MB_OK) return rc;
+    for (int attempt = 0; attempt < 3; ++attempt) {
+        const unsigned long long gen = mb::ipc_evictions();
+        for (int p = 0; p < world; ++p) {
+            if (p == rank) continue;
+            for (const ShmEntry& en : dir[p]) {
+                HTile* t = en.kind == 0 ? (en.idx >= 0 && en.idx < m * k ? &tA[en.idx] : nullptr) : (en.kind == 1 && en.idx >= 0 && en.idx < k * n ? &tB[en.idx] : nullptr);
+                if (!t || !t->need || t->home != p) continue;
+                if ((rc = open_entry(en, &t->peer)) != MB_OK) return rc;
+            }
+        }
+        if (mb::ipc_evictions() == gen) break;
+    }
+    for (auto& t : tA) if (t.need && t.home != rank && !t.peer) return fail(MB_ERR_INVALID_ARG, "mb_matmul_blocked_dist_host: a peer did not publish an A tile");
+    for (auto& t : tB) if (t.need && t.home != rank && !t.peer) return fail(MB_ERR_INVALID_ARG, "mb_matmul_blocked_dist_host: a peer did not publish a B tile");
+
+    // everything of the previous call that touches the arena / my uploads is ordered on S: fan that out
+    MB_CUDA(cudaEventRecord(c->ev_tmp, S));
+    MB_CUDA(cudaStreamWaitEvent(U, c->ev_tmp, 0));
+    MB_CUDA(cudaStreamWaitEvent(X, c->ev_tmp, 0));
+    MB_CUDA(cudaStreamWaitEvent(R, c->ev_tmp, 0));
+
+    // ---- upload stream: my tiles band by band; every band is announced locally and to the ranks that pull it ----
+    std::vector<std::vector<int>> consumers_a(m * k), consumers_b(k * n);
+    std::vector<char> consumer(world, 0), source(world, 0);
+    for (int i = 0; i < m; ++i)
+        for (int j = 0; j < n; ++j)
+            for (int kk = 0; kk < k; ++kk) {
+                const int r = plan.prod_rank[i * n * k + j * k + kk];
+                auto addc = [&](std::vector<int>& v) { if (r != rank && std::find(v.begin(), v.end(), r) == v.end()) v.push_back(r); };
+                if (a_home[i * k + kk] == rank) addc(consumers_a[i * k + kk]);
+                if (b_home[kk * n + j] == rank) addc(consumers_b[kk * n + j]);
+            }
+    for (int b = 0; b < MAX_BANDS; ++b) {
+        for (int pass = 0; pass < 2; ++pass) {
+            const int cnt = pass == 0 ? m * k : k * n;
+            for (int t = 0; t < cnt; ++t) {
+                HTile& ht = pass == 0 ? tA[t] : tB[t];
+                if (ht.home != rank || b >= ht.nbands) continue;
+                const double* src = pass == 0 ? A_host[t] : B_host[t];
+                char* dst = c->arena + ht.off;
+                const int lo = b * ht.band, hi = std::min(pass == 0 ? ht.rows : ht.cols, lo + ht.band);
+                if (pass == 0)      // A: row band [lo, hi) of every column
+                    MB_CUDA(cudaMemcpy2DAsync(dst + (size_t)lo * 8, (size_t)ht.ld * 8, src + lo, (size_t)ht.rows * 8, (size_t)(hi - lo) * 8, ht.cols,
+                                              cudaMemcpyHostToDevice, U));
+                else                // B: column band [lo, hi)
+                    MB_CUDA(cudaMemcpy2DAsync(dst + (size_t)lo * ht.ld * 8, (size_t)ht.ld * 8, src + (size_t)lo * ht.rows, (size_t)ht.rows * 8,
+                                              (size_t)ht.rows * 8, hi - lo, cudaMemcpyHostToDevice, U));
+                if (ht.need) MB_CUDA(sig(c, c->flags + F_BAND + ht.ready_base + b, e, U));
+                for (int r : (pass == 0 ? consumers_a[t] : consumers_b[t])) {
+                    MB_CUDA(sig(c, c->flags_peer[r] + F_UPREADY + (rank * UP_SLOTS + ht.slot) * MAX_BANDS + b, e, U));
+                    consumer[r] = 1;
+                }
+            }
+        }
+    }
+    // ---- pull stream: the other tiles I need, as their bands are announced ----
+    for (int b = 0; b < MAX_BANDS; ++b) {
+        for (int pass = 0; pass < 2; ++pass) {
+            const int cnt = pass == 0 ? m * k : k * n;
+            for (int t = 0; t < cnt; ++t) {
+                HTile& ht = pass == 0 ? tA[t] : tB[t];
+                if (!ht.need || ht.home == rank || b >= ht.nbands) continue;
+                source[ht.home] = 1;
+                MB_CUDA(waitf(c, c->flags + F_UPREADY + (ht.home * UP_SLOTS + ht.slot) * MAX_BANDS + b, e, X));
+                char* dst = c->arena + ht.off;
+                const int lo = b * ht.band, hi = std::min(pass == 0 ? ht.rows : ht.cols, lo + ht.band);
+                if (pass == 0)
+                    MB_CUDA(cudaMemcpy2DAsync(dst + (size_t)lo * 8, (size_t)ht.ld * 8, ht.peer + (size_t)lo * 8, (size_t)ht.ld * 8, (size_t)(hi - lo) * 8,
+                                              ht.cols, cudaMemcpyDeviceToDevice, X));
+                else
+                    MB_CUDA(cudaMemcpyAsync(dst + (size_t)lo * ht.ld * 8, ht.peer + (size_t)lo * ht.ld * 8, (size_t)(hi - lo) * ht.ld * 8,
+                                            cudaMemcpyDeviceToDevice, X));
+                MB_CUDA(sig(c, c->flags + F_BAND + ht.ready_base + b, e, X));
+            }
+        }
+    }
+    for (int p = 0; p < world; ++p)
+        if (source[p]) MB_CUDA(sig(c, flag_ch(c, p, CH_DONE, rank), e, X));
+
+    // ---- compute stream: one grouped launch over my sub-blocks in wavefront order ----
+    std::vector<char> writes_to(world, 0), reads_from(world, 0);
+    for (const MyC& mc : myc) {
+        const auto& h = plan.holders[mc.id];
+        if (h.size() == 2) { const int peer = h[0] == rank ? h[1] : h[0]; writes_to[peer] = 1; reads_from[peer] = 1; }
+    }
+    for (int p = 0; p < world; ++p)
+        if (writes_to[p] && c->last_write_epoch[p]) MB_CUDA(waitf(c, flag_ch(c, rank, CH_FREE, p), c->last_write_epoch[p], S));
+    static thread_local mb::G2Launch L;
+    L = mb::G2Launch();
+    auto op_of = [&](HTile& t, bool is_a) {
+        if (t.op >= 0) return t.op;
+        int& cnt = is_a ? L.na : L.nb;
+        mb::G2Operand& o = (is_a ? L.A : L.B)[cnt];
+        o.ptr = reinterpret_cast<const double*>(c->arena + t.off); o.ld = t.ld; o.rows = t.rows; o.cols = t.cols;
+        o.band = t.band; o.ready_base = t.ready_base;
+        return t.op = cnt++;
+    };
+    struct Sub { int id, p, q, m_off, n_off, M, N, wave, sub_idx; bool mine; int entry; };
+    std::vector<Sub> subs;
+    for (const MyC& mc : myc) {
+        int ba, nba, bb, nbb;
+        bands_of(row_len[mc.i], ba, nba); bands_of(col_len[mc.j], bb, nbb);
+        const auto& h = plan.holders[mc.id];
+        const int my_pos = h[0] == rank ? 0 : 1;
+        for (int p = 0; p < nba; ++p)
+            for (int q = 0; q < nbb; ++q) {
+                Sub sb{mc.id, p, q, p * ba, q * bb, std::min(ba, row_len[mc.i] - p * ba), std::min(bb, col_len[mc.j] - q * bb), std::max(p, q),
+                       pair_base[mc.id] + p * nbb + q, true, -1};
+                if (h.size() == 2) sb.mine = ((p + q) % 2) == my_pos;        // checkerboard: both links carry half of the tile
+                subs.push_back(sb);
+            }
+    }
+    std::stable_sort(subs.begin(), subs.end(), [](const Sub& a, const Sub& b) { return a.wave != b.wave ? a.wave < b.wave : (a.id != b.id ? a.id < b.id : (a.p != b.p ? a.p < b.p : a.q < b.q)); });
+    for (Sub& sb : subs) {
+        const int i = sb.id / n, j = sb.id % n;
+        const MyC* mc = nullptr;
+        for (const MyC& qq : myc) if (qq.id == sb.id) mc = &qq;
+        sb.entry = L.ne;
+        mb::G2Entry& en = L.E[L.ne++];
+        en.nseg = (int)mc->kks.size();
+        for (int sg = 0; sg < en.nseg; ++sg) {
+            en.a_op[sg] = op_of(tA[i * k + mc->kks[sg]], true);
+            en.b_op[sg] = op_of(tB[mc->kks[sg] * n + j], false);
+        }
+        en.m_off = sb.m_off; en.n_off = sb.n_off; en.M = sb.M; en.N = sb.N;
+        const int ldc = even(row_len[i]);
+        en.done_ctr = c->flags + F_CTR + sb.entry;
+        en.sig_val = e;
+        const auto& h = plan.holders[sb.id];
+        if (sb.mine) {
+            en.D = reinterpret_cast<double*>(c->arena + coff[sb.id]) + (size_t)sb.n_off * ldc + sb.m_off; en.ldd = ldc;
+            en.sig_local = c->flags + F_SIG + sb.entry;
+        } else {
+            const int peer = h[0] == rank ? h[1] : h[0];
+            en.D = reinterpret_cast<double*>(c->staging_peer[peer] + (size_t)rank * c->slot_bytes + slot_off[sb.id]) + (size_t)sb.n_off * ldc + sb.m_off;
+            en.ldd = ldc;
+            en.sig_remote = c->flags_peer[peer] + F_SUBDONE + rank * SUB_SLOTS + sb.sub_idx;
+        }
+    }
+    L.ready = c->flags + F_BAND; L.ready_val = e; L.status = c->flags + F_STATUS; L.timeout_ns = timeout_ns(c);
+    MB_CUDA(cudaMemsetAsync(c->flags + F_CTR, 0, sizeof(unsigned long long) * mb::G2_MAX_ENTRIES, S));
+    {
+        int launches = 0;
+        cudaError_t ce = mb::gemm_f64_grouped2(L, ctx->num_sms, S, &launches);
+        if (ce != cudaSuccess) return cuda_fail(ce, "mb_matmul_blocked_dist_host: grouped launch");
+        ctx->launches += launches;
+    }
+    MB_CUDA(cudaEventRecord(c->ev_compute, S));
+    c->have_compute = true;
+    for (int p = 0; p < world; ++p) if (writes_to[p]) c->last_write_epoch[p] = e;
+
+    // ---- reduce stream: finished sub-blocks -> (+ the peer's partial) -> host ----
+    for (const Sub& sb : subs) {
+        if (!sb.mine) continue;
+        const int i = sb.id / n;
+        const int ldc = even(row_len[i]);
+        const auto& h = plan.holders[sb.id];
+        MB_CUDA(waitf(c, c->flags + F_SIG + sb.entry, e, R));
+        double* mine_ptr = reinterpret_cast<double*>(c->arena + coff[sb.id]) + (size_t)sb.n_off * ldc + sb.m_off;
+        if (h.size() == 2) {
+            const int peer = h[0] == rank ? h[1] : h[0];
+            MB_CUDA(waitf(c, c->flags + F_SUBDONE + peer * SUB_SLOTS + sb.sub_idx, e, R));
+            const double* staged = reinterpret_cast<const double*>(c->staging + (size_t)peer * c->slot_bytes + slot_off[sb.id]) + (size_t)sb.n_off * ldc + sb.m_off;
+            MB_CUDA(mb::ew_binary(mb::EW_ADD, sb.M, sb.N, mine_ptr, 1, ldc, staged, 1, ldc, mine_ptr, 1, ldc, R));
+            ctx->launches++;
+        }
+        MB_CUDA(cudaMemcpy2DAsync(C_host[sb.id] + (size_t)sb.n_off * row_len[i] + sb.m_off, (size_t)row_len[i] * 8, mine_ptr, (size_t)ldc * 8,
+                                  (size_t)sb.M * 8, sb.N, cudaMemcpyDeviceToHost, R));
+    }
+    for (int p = 0; p < world; ++p)
+        if (reads_from[p]) MB_CUDA(sig(c, flag_ch(c, p, CH_FREE, rank), e, R));
+    // ---- my upload buffers may not be overwritten until everyone has pulled them; S is ordered behind R ----
+    for (int p = 0; p < world; ++p)
+        if (consumer[p]) MB_CUDA(waitf(c, flag_ch(c, rank, CH_DONE, p), e, S));
+    MB_CUDA(cudaEventRecord(c->ev_tmp, R));
+    MB_CUDA(cudaStreamWaitEvent(S, c->ev_tmp, 0));
+    MB_CUDA(cudaEventRecord(c->ev_tmp, U));
+    MB_CUDA(cudaStreamWaitEvent(S, c->ev_tmp, 0));
+    MB_CUDA(cudaMemcpyAsync(c->status_host, c->flags + F_STATUS, 8, cudaMemcpyDeviceToHost, S));
+    MB_CUDA(cudaStreamSynchronize(R));
+    MB_CUDA(cudaStreamSynchronize(S));
+    if (*c->status_host != 0)
+        return fail(MB_ERR_TIMEOUT, "mb_matmul_blocked_dist_host: a device-side wait for a peer timed out (a rank died or fell out of step)");
     return MB_OK;
 }
 

@@ -51,6 +51,8 @@ struct mb_block {
 namespace mb {
 cudaError_t ipc_export(const void* dptr, unsigned char handle[64], long long* offset, long long* alloc_bytes);
 cudaError_t ipc_open(const unsigned char handle[64], void** base_out);
+cudaError_t ipc_open_ex(const unsigned char handle[64], void** base_out, bool pinned);
+unsigned long long ipc_evictions();
 cudaError_t ipc_close(const unsigned char handle[64]);
 cudaError_t ipc_close_all();
 cudaError_t flag_signal(void* flag, unsigned long long v, cudaStream_t st);

@@ -7,6 +7,7 @@
 #include "../../include/marlin_b200.h"
 #include <cuda.h>
 #include <cuda_runtime.h>
+#include <atomic>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -42,7 +43,10 @@ __global__ void flag_wait_kernel(const unsigned long long* flag, unsigned long l
 }
 
 std::mutex g_mu;
-std::map<std::string, void*> g_opened;     // IPC handle bytes -> mapped base address (per process)
+struct Mapping { void* base; bool pinned; unsigned long long last_use; };
+std::map<std::string, Mapping> g_opened;   // IPC handle bytes -> mapped base address (per process)
+unsigned long long g_use_clock = 0;
+std::atomic<unsigned long long> g_evictions{0};
 
 typedef CUresult (*GetRangeFn)(CUdeviceptr*, size_t*, CUdeviceptr);
 GetRangeFn get_range_fn() {
@@ -75,20 +79,54 @@ cudaError_t ipc_export(const void* dptr, unsigned char handle[64], long long* of
     return cudaSuccess;
 }
 
-cudaError_t ipc_open(const unsigned char handle[64], void** base_out) {
+// Map a peer allocation (cached per handle).  `pinned` mappings (flag arrays, staging buffers) live until ipc_close /
+// ipc_close_all; tile mappings are evictable: an exporter that frees a tile and allocates a new one may get the same
+// physical allocation back under a NEW handle, which cudaIpcOpenMemHandle refuses while the stale mapping exists
+// (cudaErrorAlreadyMapped) — then every evictable mapping is dropped (after a device sync: nothing is in flight on
+// them) and the open is retried.  Tile mappings unused for a long time are trimmed as well.
+cudaError_t ipc_open_ex(const unsigned char handle[64], void** base_out, bool pinned) {
     std::lock_guard<std::mutex> lk(g_mu);
     std::string key(reinterpret_cast<const char*>(handle), 64);
+    ++g_use_clock;
     auto it = g_opened.find(key);
-    if (it != g_opened.end()) { *base_out = it->second; return cudaSuccess; }
+    if (it != g_opened.end()) {
+        it->second.last_use = g_use_clock;
+        it->second.pinned = it->second.pinned || pinned;
+        *base_out = it->second.base;
+        return cudaSuccess;
+    }
     cudaIpcMemHandle_t h;
     std::memcpy(&h, handle, 64);
     void* base = nullptr;
     cudaError_t e = cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e == cudaErrorAlreadyMapped) {
+        cudaGetLastError();
+        cudaDeviceSynchronize();
+        ++g_evictions;
+        for (auto jt = g_opened.begin(); jt != g_opened.end();) {
+            if (!jt->second.pinned) { cudaIpcCloseMemHandle(jt->second.base); jt = g_opened.erase(jt); }
+            else ++jt;
+        }
+        e = cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess);
+    }
     if (e != cudaSuccess) return e;
-    g_opened[key] = base;
+    g_opened[key] = Mapping{base, pinned, g_use_clock};
     *base_out = base;
+    if (g_opened.size() > 256) {                     // trim tile mappings that have not been used for a while
+        bool synced = false;
+        for (auto jt = g_opened.begin(); jt != g_opened.end();) {
+            if (!jt->second.pinned && jt->second.last_use + 4096 < g_use_clock) {
+                if (!synced) { cudaDeviceSynchronize(); synced = true; ++g_evictions; }
+                cudaIpcCloseMemHandle(jt->second.base);
+                jt = g_opened.erase(jt);
+            } else ++jt;
+        }
+    }
     return cudaSuccess;
 }
+cudaError_t ipc_open(const unsigned char handle[64], void** base_out) { return ipc_open_ex(handle, base_out, false); }
+// Bumped whenever evictable mappings were dropped: pointers obtained from ipc_open before that are stale.
+unsigned long long ipc_evictions() { return g_evictions.load(); }
 
 // Unmap one peer allocation (the exporter is about to free it, e.g. a staging buffer being regrown).
 cudaError_t ipc_close(const unsigned char handle[64]) {
@@ -96,14 +134,14 @@ cudaError_t ipc_close(const unsigned char handle[64]) {
     std::string key(reinterpret_cast<const char*>(handle), 64);
     auto it = g_opened.find(key);
     if (it == g_opened.end()) return cudaSuccess;
-    cudaError_t e = cudaIpcCloseMemHandle(it->second);
+    cudaError_t e = cudaIpcCloseMemHandle(it->second.base);
     g_opened.erase(it);
     return e;
 }
 
 cudaError_t ipc_close_all() {
     std::lock_guard<std::mutex> lk(g_mu);
-    for (auto& kv : g_opened) cudaIpcCloseMemHandle(kv.second);
+    for (auto& kv : g_opened) cudaIpcCloseMemHandle(kv.second.base);
     g_opened.clear();
     return cudaSuccess;
 }

@@ -9,8 +9,13 @@ from pathlib import Path
 
 import numpy as np
 
-sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
-from marlin_b200 import _native as nat          # noqa: E402  (ctypes declarations only)
+ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT))
+import importlib.util                            # noqa: E402
+# the ctypes declarations only — loaded by path, because importing the marlin_b200 PACKAGE would pull in torch
+_spec = importlib.util.spec_from_file_location("mb_native_standalone", ROOT / "marlin_b200" / "_native.py")
+nat = importlib.util.module_from_spec(_spec)
+_spec.loader.exec_module(nat)
 from oracle import reference_model as rm        # noqa: E402
 
 
@@ -104,6 +109,58 @@ def main():
                 for h in arr:
                     if h:
                         nat.check(lib.mb_block_free(ctx, h))
+    # ---- the end-to-end entry: HOST tiles in, HOST tiles out (mb_matmul_blocked_dist_host), C tiles in shared pinned memory ----
+    host_cases = [(1300, 520, 1400, 1, 2, 1), (300, 260, 212, 2, 2, 2), (1100, 2100, 1200, 2, 2, 2), (2304, 1040, 1100, 1, 2, 1)]
+    for ci, (M, K, N, m, k, n) in enumerate(host_cases):
+        A, B = rng.random((M, K)) - 0.5, rng.random((K, N)) - 0.5
+        oa = rm.DenseVecMatrix(list(enumerate(A))).to_block_matrix(m, k)
+        ob = rm.DenseVecMatrix(list(enumerate(B))).to_block_matrix(k, n)
+        ta, tb = dict(oa.blocks), dict(ob.blocks)
+        ref = dict(oa.multiply(ob, gemm="blas").blocks)
+        a_home = (C.c_int32 * (m * k))()
+        b_home = (C.c_int32 * (k * n))()
+        nat.check(lib.mb_dist_host_homes(m, k, n, world, a_home, b_home))
+        loads = [0] * world
+        for h in list(a_home) + list(b_home):
+            loads[h] += 1
+        assert max(loads) - min(loads) <= 1 or world > m * k + k * n, loads          # uploads spread over the PCIe links
+        pr = (C.c_int32 * (m * k * n))()
+        co = (C.c_int32 * (m * n))()
+        nat.check(lib.mb_dist_plan(m, k, n, world, pr, co))
+        a_np = {t: np.asfortranarray(ta[(t // k, t % k)]) for t in range(m * k) if a_home[t] == rank}
+        b_np = {t: np.asfortranarray(tb[(t // n, t % n)]) for t in range(k * n) if b_home[t] == rank}
+        pa = (C.c_void_p * (m * k))(*[a_np[t].ctypes.data if t in a_np else None for t in range(m * k)])
+        pb = (C.c_void_p * (k * n))(*[b_np[t].ctypes.data if t in b_np else None for t in range(k * n)])
+        row_len = (C.c_int32 * m)(*[ta[(i, 0)].shape[0] for i in range(m)])
+        k_len = (C.c_int32 * k)(*[ta[(0, kk)].shape[1] for kk in range(k)])
+        col_len = (C.c_int32 * n)(*[tb[(0, j)].shape[1] for j in range(n)])
+        mine = sorted({(s // k) // n * n + (s // k) % n for s in range(m * k * n) if pr[s] == rank})     # C tiles I hold a partial of
+        pc = (C.c_void_p * (m * n))()
+        shared = {}
+        for t in mine:
+            ptr = C.c_void_p()
+            nbytes = int(row_len[t // n]) * int(col_len[t % n]) * 8
+            nat.check(lib.mb_host_alloc_shared(f"{session}_{ci}_{t}".encode(), nbytes, C.byref(ptr)))
+            shared[t] = (ptr, nbytes)
+            pc[t] = ptr
+        for rep in range(2):
+            for t in mine:
+                if co[t] == rank:
+                    C.memset(shared[t][0], 0xFF, shared[t][1])           # NaN pattern; every byte must be overwritten
+            nat.check(lib.mb_comm_barrier(comm))
+            nat.check(lib.mb_matmul_blocked_dist_host(comm, pa, a_home, pb, b_home, m, k, n, row_len, k_len, col_len, pc))
+            nat.check(lib.mb_comm_barrier(comm))                         # both holders have written their sub-blocks
+            for t in mine:
+                i, j = divmod(t, n)
+                got = np.ctypeslib.as_array(C.cast(shared[t][0], C.POINTER(C.c_double)), shape=(col_len[j], row_len[i])).T
+                Ai = np.hstack([ta[(i, kk)] for kk in range(k)])
+                Bj = np.vstack([tb[(kk, j)] for kk in range(k)])
+                err = (np.abs(got - ref[(i, j)]) / (np.abs(Ai) @ np.abs(Bj))).max()
+                assert err <= 1e-10, ("host", M, K, N, m, k, n, i, j, rep, err)
+                worst = max(worst, err)
+            nat.check(lib.mb_comm_barrier(comm))
+        for t in mine:
+            nat.check(lib.mb_host_free_shared(f"{session}_{ci}_{t}".encode(), shared[t][0], shared[t][1], 1 if co[t] == rank else 0))
     nat.check(lib.mb_comm_barrier(comm))
     nat.check(lib.mb_comm_destroy(comm))
     nat.check(lib.mb_shutdown(ctx))
