@@ -335,6 +335,95 @@ def freivalds_rows(A_rows, B, C_rows, ws, tol, probes=3):
             "method": "Freivalds on device per row shard: C v vs A (B v) with torch/cuBLAS dgemv; max_i |y-z|_i / (|A||B||v|)_i, worst rank"}
 
 
+# ------------------------------------------------------------------------------------------ the other BASELINE configs
+def measure_extra(kind: str, ws: int, rank: int, local_rank: int):
+    """One of BASELINE.json's other configurations, measured in the same run as the headline so that the driver's
+    record carries it: 'cfg1' = configs[1] (4096^2 fp64, one block), 'cfg3' = configs[3] (1048576x1024 x 1024x1024 fp64,
+    row-sharded), 'cfg4' = configs[4] (65536^2 bf16, 4x4 grid).  Device-timed like the headline (CUDA events, max over
+    ranks, >= 3 warm-up steps, ~1 s timed region so the clock sampler sees it), with its own parity and clocks."""
+    import math
+    import torch
+    import torch.distributed as dist
+    import marlin_b200 as mb
+    from marlin_b200 import _native as nat
+    peaks = {}
+    try:
+        peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
+    except Exception:
+        pass
+    if kind == "cfg1":
+        N, g, dt, name = 4096, 1, nat.MB_F64, "4096x4096 fp64 dense multiply, single block [BASELINE.json configs[1]]"
+        A = mb.MTUtils.randomBlockMatrix(None, N, N, g, g, seed=42)
+        B = mb.MTUtils.randomBlockMatrix(None, N, N, g, g, seed=43)
+        flops, active = 2.0 * N ** 3, 1
+        peak, peak_src, tol = FP64_PEAK_TFLOPS_MEASURED, "measured fp64 DMMA issue peak (scripts/dmma_bench.cu)", 1e-10
+        kernel = "gemm_f64_dmma_grouped_kernel (DMMA.8x8x4 + TMA)"
+    elif kind == "cfg3":
+        rows_total, kdim = 1048576, 1024
+        name = "DenseVecMatrix 1048576x1024 (row-sharded) x replicated 1024x1024, fp64 [BASELINE.json configs[3]]"
+        A = mb.MTUtils.randomDenVecMatrix(None, rows_total, kdim, numPartitions=ws, seed=42)
+        B = mb.SubMatrix(mb.MTUtils.randomBlockMatrix(None, kdim, kdim, 1, 1, seed=43).toBreeze())
+        flops, active = 2.0 * rows_total * kdim * kdim, ws
+        peak, peak_src, tol = FP64_PEAK_TFLOPS_MEASURED, "measured fp64 DMMA issue peak (scripts/dmma_bench.cu)", 1e-10
+        kernel = "gemm_f64_dmma_kernel<T,N> (row-major C = A*B as C^T = B^T*A^T; DMMA.8x8x4 + TMA)"
+    elif kind == "cfg4":
+        N, g, dt = 65536, 4, nat.MB_BF16
+        name = "65536x65536 bf16 BlockMatrix multiply, 4x4 block grid, fp32 accumulate / fp32 C tiles [BASELINE.json configs[4]]"
+        A = mb.MTUtils.randomBlockMatrix(None, N, N, g, g, seed=42, dtype=dt)
+        B = mb.MTUtils.randomBlockMatrix(None, N, N, g, g, seed=43, dtype=dt)
+        flops, active = 2.0 * N ** 3, ws
+        peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
+        peak_src, tol = "MEASURED_PEAKS.json bf16_tflops_sustained (cuBLAS bf16, seconds-long loop; burst: %s)" % peaks.get("bf16_tflops"), 1e-4
+        kernel = "gemm_bf16_tcgen05_kernel (tcgen05.mma kind::f16 + TMEM + TMA), K segments over kk in one launch per C tile"
+    else:
+        raise ValueError(kind)
+    torch.cuda.synchronize()
+
+    def sync():
+        if ws > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    Cm = None
+    for _ in range(3):
+        del Cm
+        Cm = A.multiply(B)
+    sync()
+    e0.record()
+    del Cm
+    Cm = A.multiply(B)
+    e1.record()
+    sync()
+    est = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
+    if ws > 1:
+        dist.all_reduce(est, op=dist.ReduceOp.MAX)
+    steps = int(min(200, max(3, math.ceil(1000.0 / max(float(est.item()), 1e-3)))))
+    sync()
+    e0.record()
+    for _ in range(steps):
+        del Cm
+        Cm = A.multiply(B)
+    e1.record()
+    sync()
+    t = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
+    if ws > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item()) / steps
+    clocks = sampler.stop() if rank == 0 else None
+    value = flops / (ms * 1e-3) / 1e12
+    parity = freivalds_rows(A.data, B, Cm.data, ws, tol) if kind == "cfg3" else freivalds_blockmatrix(A, B, Cm, ws, tol)
+    del Cm, A, B
+    torch.cuda.empty_cache()
+    return {"config": name, "metric": "dense multiply throughput (2*M*K*N flop)", "value": value, "unit": "TFLOP/s", "ms_per_step": ms,
+            "steps": steps, "warmup": 4, "n_gpus": ws, "dtype": "bf16" if kind == "cfg4" else "f64",
+            "roofline": {"bound": "tensor", "achieved": value / active, "peak": peak, "unit": "TFLOP/s", "frac": value / active / peak,
+                         "kernel": kernel, "peak_source": peak_src, "gpus_doing_work": active}, "parity": parity, "clocks": clocks}
+
+
 # ------------------------------------------------------------------------------------------ GPU arm
 def run_ours(args):
     import numpy as np
@@ -448,8 +537,9 @@ def run_ours(args):
                 "frac": (achieved / peak) if achieved else None, "traffic": traffic,
                 "kernel": ("gemm_bf16_tcgen05_kernel<N,N> (tcgen05.mma kind::f16 + TMEM + TMA)" if bf16 else
                            ("gemm_f64_dmma_kernel<T,N> (row-major C = A*B as C^T = B^T*A^T)" if tall else
-                            ("gemm_f64_dmma_grouped_kernel" if launches_per_step < local_products else "gemm_f64_dmma_kernel<N,N>")
-                            + " (DMMA.8x8x4 + TMA)")), "launch_ms_avg": gemm_avg_ms,
+                            "gemm_f64_dmma_grouped_kernel (DMMA.8x8x4 + TMA; one launch per rank and step" +
+                            ("" if ws == 1 else "; at N > 1 the timed span also holds the flag kernels of the exchange protocol and any wait for tiles / the peer's partial") + ")")),
+                "launch_ms_avg": gemm_avg_ms,
                 "flops_per_launch": flops_per_launch, "launches_per_step": launches_per_step,
                 "peak_source": peak_src or "measured fp64 DMMA issue peak on this pool's B200 (scripts/dmma_bench.cu, "
                                "profiles/r01_probe_dmma_peak_and_gemm_v1.log); MEASURED_PEAKS.json carries no fp64 entry; "
@@ -503,23 +593,74 @@ def run_ours(args):
             def e2e_step():
                 nat.check(rt.lib.mb_matmul_blocked_host(rt.ctx, pa, pb, g, g, g, lens, lens, lens, pc))
         else:
-            path = "pinned host blocks -> H2D -> BlockMatrix.multiply (NCCL tile exchange) -> D2H of owned C blocks, every step"
+            # N > 1: the C-ABI end-to-end entry (mb_matmul_blocked_dist_host).  Every input tile sits in pinned host memory on
+            # ONE of the ranks that need it (mb_dist_host_homes spreads the uploads over the PCIe links), C tiles are shared
+            # pinned host arrays that the ranks computing a tile fill together; every step uploads all of A and B and
+            # downloads all of C.
+            from marlin_b200 import peer
+            from marlin_b200.utils.mt_utils import MTUtils, UniformGenerator
+            mesh = peer.PeerMesh.get()
+            if mesh is None:
+                raise SystemExit("the e2e leg at N > 1 needs the peer-memory communicator (mb_comm_init failed)")
+            lib = rt.lib
+            gk = g
+            a_home = (C.c_int32 * (g * gk))()
+            b_home = (C.c_int32 * (gk * g))()
+            nat.check(lib.mb_dist_host_homes(g, gk, g, ws, a_home, b_home))
+            prank, cown = mesh.plan(g, gk, g)
+            bs_ = N // g
+            seeds_a, seeds_b = MTUtils._partition_seeds(42, g * g), MTUtils._partition_seeds(43, g * g)
+            keep = []
+
+            def host_tile(seed):
+                blk = mb.SubMatrix.empty(bs_, bs_, nat.MB_F64)
+                MTUtils._fill(blk, seed, 0, UniformGenerator(0.0, 1.0), row_major=False)      # the same values A / B hold on the device
+                t_ = torch.empty(bs_ * bs_, dtype=torch.float64).pin_memory()
+                t_.copy_(blk.buf[: bs_ * bs_])
+                keep.append(t_)
+                return t_.data_ptr()
+
+            pa = (C.c_void_p * (g * gk))(*[host_tile(seeds_a[t]) if a_home[t] == rank else None for t in range(g * gk)])
+            pb = (C.c_void_p * (gk * g))(*[host_tile(seeds_b[t]) if b_home[t] == rank else None for t in range(gk * g)])
+            torch.cuda.synchronize()
+            my_c = sorted({s // gk for s in range(g * gk * g) if prank[s] == rank})
+            box = [os.urandom(6).hex() if rank == 0 else None]
+            dist.broadcast_object_list(box, src=0)
+            pc = (C.c_void_p * (g * g))()
+            shared = {}
+            for t in my_c:
+                ptr = C.c_void_p()
+                nat.check(lib.mb_host_alloc_shared(f"{box[0]}_c{t}".encode(), bs_ * bs_ * 8, C.byref(ptr)))
+                shared[t] = ptr
+                pc[t] = ptr
+            lens = (C.c_int32 * g)(*([bs_] * g))
+            h2d = sum(bs_ * bs_ * 8 for t in range(g * gk) if a_home[t] == rank) + sum(bs_ * bs_ * 8 for t in range(gk * g) if b_home[t] == rank)
+            # bytes this rank downloads: whole tiles it holds alone, half of the tiles it shares (checkerboard of sub-blocks)
+            holders = {}
+            for s_ in range(g * gk * g):
+                holders.setdefault(s_ // gk, set()).add(prank[s_])
+            d2h_box[0] = sum(bs_ * bs_ * 8 // len(holders[t]) for t in my_c)
+            path = ("mb_matmul_blocked_dist_host (C ABI): pinned host tiles -> banded H2D on the rank that homes a tile + NVLink pulls by "
+                    "the others -> one grouped DMMA launch per rank (starts on the first bands) -> per-sub-block reduce + D2H into shared "
+                    "pinned C tiles, every step")
 
             def e2e_step():
-                da = [(b, mb.SubMatrix(buf=t_.to(rt.device, non_blocking=True), rows=r, cols=c)) for b, t_, r, c in host_a]
-                db = [(b, mb.SubMatrix(buf=t_.to(rt.device, non_blocking=True), rows=r, cols=c)) for b, t_, r, c in host_b]
-                Ad = mb.BlockMatrix(da, N, N, g, g)
-                Bd = mb.BlockMatrix(db, N, N, g, g)
-                Cd = Ad.multiply(Bd)
-                nbytes = 0
-                for b, s in Cd.blocks:
-                    key = (b.row, b.column)
-                    if key not in host_c:
-                        host_c[key] = torch.empty(s.rows * s.cols, dtype=torch.float64).pin_memory()
-                    host_c[key].copy_(s.buf[: s.rows * s.cols], non_blocking=True)
-                    nbytes += s.rows * s.cols * 8
-                d2h_box[0] = nbytes
+                nat.check(lib.mb_matmul_blocked_dist_host(mesh.comm, pa, a_home, pb, b_home, g, gk, g, lens, lens, lens, pc))
+
+            def e2e_check():
+                """The e2e result against the device-resident result of the same multiply (owner ranks, whole tiles)."""
+                Cdev = {(b.row, b.column): s_ for b, s_ in A.multiply(B).blocks}
                 torch.cuda.synchronize()
+                dist.barrier()
+                worst = torch.zeros(1, device="cuda", dtype=torch.float64)
+                for t in my_c:
+                    i, j = divmod(t, g)
+                    if (i, j) in Cdev:
+                        host = np.ctypeslib.as_array(C.cast(shared[t], C.POINTER(C.c_double)), shape=(bs_ * bs_,))
+                        d = (torch.from_numpy(host).to(rt.device) - Cdev[(i, j)].buf[: bs_ * bs_]).abs().max()
+                        worst = torch.maximum(worst, d.reshape(1))
+                dist.all_reduce(worst, op=dist.ReduceOp.MAX)
+                return float(worst.item())
 
     if not args.no_e2e:
         e2e_steps = max(2, min(args.steps, 3))
@@ -541,6 +682,9 @@ def run_ours(args):
         e2e_ms = float(t.item()) / e2e_steps
         e2e = {"value": flops / (e2e_ms * 1e-3) / 1e12, "unit": "TFLOP/s", "h2d_bytes_per_step": int(bts[0].item()),
                "d2h_bytes_per_step": int(bts[1].item()), "ms_per_step": e2e_ms, "steps": e2e_steps, "path": path}
+        if ws > 1 and not tall:
+            e2e["max_abs_diff_vs_device_result"] = e2e_check()
+            e2e["fraction_of_device_value"] = e2e["value"] / value
 
     # ---- extra (not the headline): the same multiply with the block GEMMs on the int8 tensor cores ----
     int8_split = None
@@ -584,6 +728,18 @@ def run_ours(args):
             parity = freivalds_blockmatrix(A, B, Cm, ws, tol)
     del Cm
 
+    # ---- the other BASELINE configurations, in the same run (only next to the default headline workload) ----
+    extra_configs = None
+    if not args.no_extra_configs and not tall and not bf16 and (N, g) == (16384, 2):
+        del A, B
+        torch.cuda.empty_cache()
+        extra_configs = {}
+        for kind in ("cfg1", "cfg3", "cfg4"):
+            try:
+                extra_configs[kind] = measure_extra(kind, ws, rank, local_rank)
+            except Exception as exc:            # never let an extra break the headline line
+                extra_configs[kind] = {"error": str(exc)[:300]}
+
     cpu_baseline = None
     if rank == 0 and not args.no_cpu_baseline:
         r = cpu_port_sample(N, g, args.cpu_seconds, tall=tall)
@@ -601,7 +757,7 @@ def run_ours(args):
             "data": "synthetic",
             "config": workload_config(args, ws),
             "roofline": roofline, "e2e": e2e, "parity": parity, "cpu_baseline": cpu_baseline, "gpu_launches": int(launches),
-            "fp64_on_int8_tensor_cores": int8_split,
+            "fp64_on_int8_tensor_cores": int8_split, "extra_configs": extra_configs,
             "clocks": clocks,
             "phases_ms_per_step": {k: v[0] / args.steps for k, v in phases.items()},
             "pct_of_tensor_peak": 100.0 * value / (peak * ws),
