@@ -146,6 +146,22 @@ int32_t mb_block_dot(mb_ctx* ctx, const mb_block* x, const mb_block* y, double* 
  * -> Breeze `v * w.t` -> dgemm with k = 1. */
 int32_t mb_block_ger(mb_ctx* ctx, const mb_block* x, const mb_block* y, mb_block* out);
 
+/* ---- f4: the local step of DenseVecMatrix.luDecompose / choleskyDecompose / inverse
+ *      (matrix/DenseVecMatrix.scala:283-466, 475-561, 568-764), which the reference hands to Breeze -> LAPACK
+ *      (brzLU = dgetrf, brzCholesky = dpotrf, brzInv = dgetrf + dgetri, `\` = triangular / general solves).
+ *      Recursive on the device: the flops run in the DMMA GEMM, the leaves in small panel kernels. ---- */
+/* In place: unit-lower L and U packed like dgetrf; perm_out (rows entries, host, may be NULL) receives the reference's
+ * permutation array: row i of L*U is row perm_out[i] of A.  A singular pivot is not an error (as with brzLU). */
+int32_t mb_block_lu(mb_ctx* ctx, mb_block* A, int32_t* perm_out);
+/* In place: L (lower, A = L L^T), strict upper triangle zeroed (Breeze `cholesky`); reads the lower triangle only.
+ * MB_ERR_CUDA ("not positive definite") if a pivot is not positive. */
+int32_t mb_block_cholesky(mb_ctx* ctx, mb_block* A);
+/* out = A^-1 (partial-pivoting LU + two triangular solves of the permuted identity); MB_ERR_CUDA if exactly singular. */
+int32_t mb_block_inverse(mb_ctx* ctx, const mb_block* A, mb_block* out);
+/* T X = B in place (B := X), T triangular (lower / upper, unit or explicit diagonal); with transposed views of T and B
+ * this also covers X T = B.  Used for `l \ b` and `b * inv(u)` of the block algorithms. */
+int32_t mb_block_trsm(mb_ctx* ctx, const mb_block* T, int32_t lower, int32_t unit_diagonal, mb_block* B);
+
 /* ---- a11: MTUtils.randomDenVecMatrix / randomBlockMatrix input generation
  *      (utils/MTUtils.scala:34-73, rdd/RandomRDD.scala:28-101, utils/RandomDataGenerator.scala:53-65,113-131).
  * Fills `count` consecutive values of partition stream `partition_seed` (one XORShift stream per

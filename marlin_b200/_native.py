@@ -71,6 +71,10 @@ SIGNATURES = {
     "mb_block_gemv": (c_i32, [c_ctx, c_blk, c_blk, c_blk, c_i32]),
     "mb_block_dot": (c_i32, [c_ctx, c_blk, c_blk, c_dp]),
     "mb_block_ger": (c_i32, [c_ctx, c_blk, c_blk, c_blk]),
+    "mb_block_lu": (c_i32, [c_ctx, c_blk, C.POINTER(c_i32)]),
+    "mb_block_cholesky": (c_i32, [c_ctx, c_blk]),
+    "mb_block_inverse": (c_i32, [c_ctx, c_blk, c_blk]),
+    "mb_block_trsm": (c_i32, [c_ctx, c_blk, c_i32, c_i32, c_blk]),
     "mb_fill_uniform": (c_i32, [c_ctx, c_blk, c_i64, c_i64, c_f64, c_f64, c_i32]),
     "mb_hash_seed": (c_i64, [c_i64]),
     "mb_partition_seeds": (c_i32, [c_i64, c_i32, C.POINTER(c_i64)]),

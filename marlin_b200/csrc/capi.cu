@@ -7,6 +7,7 @@
 #include "gemm_bf16.h"
 #include "gemm_ozaki.h"
 #include "blas12.h"
+#include "factor.h"
 
 #include <cuda_runtime.h>
 #include <algorithm>
@@ -178,6 +179,8 @@ int32_t mb_shutdown(mb_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     if (ctx->scratch) cudaFree(ctx->scratch);
     if (ctx->vec_ws) cudaFree(ctx->vec_ws);
+    if (ctx->int_ws) cudaFree(ctx->int_ws);
+    if (ctx->int_host) cudaFreeHost(ctx->int_host);
     if (ctx->host_scalar) cudaFreeHost(ctx->host_scalar);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
@@ -1041,6 +1044,120 @@ int32_t mb_block_ger(mb_ctx* ctx, const mb_block* x, const mb_block* y, mb_block
     if (out->is_transpose) std::swap(xv, yv);       // (x y^T)^T = y x^T in the array underneath
     MB_CUDA(mb::ger_f64(xv.len, yv.len, xv.p, xv.inc, yv.p, yv.inc, f64_ptr(out), out->ld, ctx->stream));
     ctx->launches++;
+    return MB_OK;
+}
+
+// ---------------------------------------------------------------------- factorizations
+static int32_t int_scratch(mb_ctx* ctx, size_t count) {
+    if (count > ctx->int_ws_count) {
+        if (ctx->int_ws) { MB_CUDA(cudaStreamSynchronize(ctx->stream)); cudaFree(ctx->int_ws); ctx->int_ws = nullptr; ctx->int_ws_count = 0; }
+        MB_CUDA(cudaMalloc(&ctx->int_ws, count * sizeof(int)));
+        ctx->int_ws_count = count;
+    }
+    if (count > ctx->int_host_count) {
+        if (ctx->int_host) { cudaFreeHost(ctx->int_host); ctx->int_host = nullptr; ctx->int_host_count = 0; }
+        MB_CUDA(cudaMallocHost(&ctx->int_host, count * sizeof(int)));
+        ctx->int_host_count = count;
+    }
+    return MB_OK;
+}
+static mb::FView fview(const mb_block* b) { return mb::FView{f64_ptr(b), rs(b), cs(b), b->rows, b->cols}; }
+
+int32_t mb_block_lu(mb_ctx* ctx, mb_block* A, int32_t* perm_out) {
+    MB_CTX(ctx);
+    MB_LOCK(ctx);
+    if (!A) return fail(MB_ERR_INVALID_ARG, "mb_block_lu: null block");
+    if (A->dtype != MB_F64) return fail(MB_ERR_UNSUPPORTED, "mb_block_lu: fp64 blocks only");
+    const int m = A->rows, n = A->cols;
+    if (m == 0 || n == 0) return MB_OK;
+    int32_t r = int_scratch(ctx, (size_t)2 * m + 8);
+    if (r) return r;
+    int *piv = ctx->int_ws, *perm = ctx->int_ws + m, *info = ctx->int_ws + 2 * m;
+    int launches = 0;
+    // rows that are never a pivot position keep themselves: start from the identity interchange
+    std::vector<int> ident(m);
+    for (int i = 0; i < m; ++i) ident[i] = i;
+    std::memcpy(ctx->int_host, ident.data(), sizeof(int) * m);
+    MB_CUDA(cudaMemcpyAsync(piv, ctx->int_host, sizeof(int) * m, cudaMemcpyHostToDevice, ctx->stream));
+    MB_CUDA(cudaStreamSynchronize(ctx->stream));
+    MB_CUDA(mb::getrf(fview(A), piv, nullptr, info, ctx->num_sms, ctx->stream, &launches));
+    ctx->launches += launches;
+    MB_CUDA(cudaMemcpyAsync(ctx->int_host, piv, sizeof(int) * (2 * (size_t)m + 1), cudaMemcpyDeviceToHost, ctx->stream));
+    MB_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (perm_out) {
+        // the reference's pArray (matrix/DenseVecMatrix.scala:303-308): apply the interchanges to 0..m-1
+        for (int i = 0; i < m; ++i) perm_out[i] = i;
+        for (int i = 0; i < std::min(m, n); ++i) std::swap(perm_out[i], perm_out[ctx->int_host[i]]);
+    }
+    (void)perm;
+    // like Breeze's LU (dgetrf), an exactly singular pivot is not an error here: U carries the zero
+    return MB_OK;
+}
+
+int32_t mb_block_cholesky(mb_ctx* ctx, mb_block* A) {
+    MB_CTX(ctx);
+    MB_LOCK(ctx);
+    if (!A) return fail(MB_ERR_INVALID_ARG, "mb_block_cholesky: null block");
+    if (A->dtype != MB_F64) return fail(MB_ERR_UNSUPPORTED, "mb_block_cholesky: fp64 blocks only");
+    if (A->rows != A->cols) return fail(MB_ERR_DIM_MISMATCH, "Cholesky needs a square matrix: %d x %d", A->rows, A->cols);
+    if (A->rows == 0) return MB_OK;
+    int32_t r = int_scratch(ctx, 8);
+    if (r) return r;
+    int launches = 0;
+    MB_CUDA(mb::potrf_lower(fview(A), ctx->int_ws, ctx->num_sms, ctx->stream, &launches));
+    ctx->launches += launches;
+    MB_CUDA(cudaMemcpyAsync(ctx->int_host, ctx->int_ws, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    MB_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (ctx->int_host[0] != 0)      // Breeze: NotConvergedException / MatrixNotSymmetricException family -> RuntimeException
+        return fail(MB_ERR_CUDA, "Cholesky: the matrix is not positive definite (leading minor %d)", ctx->int_host[0]);
+    return MB_OK;
+}
+
+int32_t mb_block_inverse(mb_ctx* ctx, const mb_block* A, mb_block* out) {
+    MB_CTX(ctx);
+    MB_LOCK(ctx);
+    if (!A || !out) return fail(MB_ERR_INVALID_ARG, "mb_block_inverse: null block");
+    if (A->dtype != MB_F64 || out->dtype != MB_F64) return fail(MB_ERR_UNSUPPORTED, "mb_block_inverse: fp64 blocks only");
+    if (A->rows != A->cols) return fail(MB_ERR_DIM_MISMATCH, "Inversion only support square matrix: %d v.s %d", A->rows, A->cols);
+    if (out->rows != A->rows || out->cols != A->cols) return fail(MB_ERR_DIM_MISMATCH, "mb_block_inverse: result block is %dx%d", out->rows, out->cols);
+    const int n = A->rows;
+    if (n == 0) return MB_OK;
+    int32_t r = int_scratch(ctx, (size_t)2 * n + 8);
+    if (r) return r;
+    // working copy of A for the factors (packed, even leading dimension)
+    const int ld = (n + 1) & ~1;
+    double* lu = nullptr;
+    MB_CUDA(cudaMalloc(&lu, (size_t)ld * n * sizeof(double)));
+    mb_block tmp;
+    tmp.data = lu; tmp.rows = n; tmp.cols = n; tmp.ld = ld; tmp.dtype = MB_F64; tmp.device = ctx->device;
+    r = copy_convert(ctx, A, &tmp);
+    if (r) { cudaFree(lu); return r; }
+    int *piv = ctx->int_ws, *info = ctx->int_ws + 2 * n;
+    int launches = 0;
+    cudaError_t e = mb::getrf(fview(&tmp), piv, nullptr, info, ctx->num_sms, ctx->stream, &launches);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(ctx->int_host, info, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e == cudaSuccess && ctx->int_host[0] != 0) {
+        cudaFree(lu);
+        return fail(MB_ERR_CUDA, "matrix is singular (zero pivot in column %d)", ctx->int_host[0] - 1);   // Breeze: MatrixSingularException
+    }
+    if (e == cudaSuccess) e = mb::inverse_from_lu(fview(&tmp), piv, fview(out), ctx->num_sms, ctx->stream, &launches);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(lu);
+    ctx->launches += launches;
+    if (e != cudaSuccess) return cuda_fail(e, "mb_block_inverse");
+    return MB_OK;
+}
+
+int32_t mb_block_trsm(mb_ctx* ctx, const mb_block* T, int32_t lower, int32_t unit_diagonal, mb_block* B) {
+    MB_CTX(ctx);
+    if (!T || !B) return fail(MB_ERR_INVALID_ARG, "mb_block_trsm: null block");
+    if (T->dtype != MB_F64 || B->dtype != MB_F64) return fail(MB_ERR_UNSUPPORTED, "mb_block_trsm: fp64 blocks only");
+    if (T->rows != T->cols || T->rows != B->rows)
+        return fail(MB_ERR_DIM_MISMATCH, "mb_block_trsm: triangle is %dx%d, right-hand side has %d rows", T->rows, T->cols, B->rows);
+    int launches = 0;
+    MB_CUDA(mb::trsm_left(fview(T), lower != 0, unit_diagonal != 0, fview(B), ctx->num_sms, ctx->stream, &launches));
+    ctx->launches += launches;
     return MB_OK;
 }
 

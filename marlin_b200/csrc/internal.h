@@ -31,6 +31,11 @@ struct mb_ctx {
     // partial vectors of the matrix x vector kernels (grow-only)
     double* vec_ws = nullptr;
     size_t vec_ws_doubles = 0;
+    // pivots / permutation / info of the factorization entries (grow-only) + a pinned mirror for the results
+    int* int_ws = nullptr;
+    size_t int_ws_count = 0;
+    int* int_host = nullptr;
+    size_t int_host_count = 0;
     // Entry points that use the context's own scratch buffers, workspaces, events or copy streams take this lock, so
     // threads sharing one context (Spark local[N] task threads) serialise there; kernel-only entries (gemm, element-wise,
     // transpose, fill) touch no shared host state and need none.  Threads that want concurrency use one context each.

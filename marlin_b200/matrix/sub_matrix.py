@@ -219,6 +219,37 @@ class SubMatrix:
         nat.check(rt.lib.mb_block_ger(rt.ctx, self.handle(), other.handle(), out.handle()))
         return out
 
+    # ---- factorizations: the Breeze/LAPACK calls of DenseVecMatrix.luDecompose / choleskyDecompose / inverse ----
+    def lu(self):
+        """`brzLU(m)` (matrix/DenseVecMatrix.scala:302): (packed unit-lower L and U, permutation array with the
+        reference's meaning: row i of L*U is row perm[i] of this block)."""
+        rt = Runtime.get(); rt.sync_stream()
+        out = self.copy()
+        perm = (C.c_int32 * max(1, self._rows))()
+        nat.check(rt.lib.mb_block_lu(rt.ctx, out.handle(), perm))
+        return out, np.array(perm[: self._rows], dtype=np.int64)
+
+    def cholesky(self) -> "SubMatrix":
+        """`brzCholesky(m)` (:495,513): lower L with L L^T = this, zeros above the diagonal."""
+        rt = Runtime.get(); rt.sync_stream()
+        out = self.copy()
+        nat.check(rt.lib.mb_block_cholesky(rt.ctx, out.handle()))
+        return out
+
+    def inverse(self) -> "SubMatrix":
+        """`brzInv(m)` (:587,606)."""
+        rt = Runtime.get(); rt.sync_stream()
+        out = SubMatrix.empty(self._rows, self._cols, nat.MB_F64, self.buf.device)
+        nat.check(rt.lib.mb_block_inverse(rt.ctx, self.handle(), out.handle()))
+        return out
+
+    def solveTriangular(self, rhs: "SubMatrix", lower: bool, unit: bool = False) -> "SubMatrix":
+        """`this \\ rhs` for a triangular `this` (the `l \\ ...` of :364): returns X with this * X = rhs."""
+        rt = Runtime.get(); rt.sync_stream()
+        x = rhs.copy()
+        nat.check(rt.lib.mb_block_trsm(rt.ctx, self.handle(), int(lower), int(unit), x.handle()))
+        return x
+
     def add_(self, other: "SubMatrix") -> "SubMatrix":
         """In-place accumulate (the reduceByKey combine of BlockMatrix.scala:177 without a new allocation)."""
         rt = Runtime.get(); rt.sync_stream()
