@@ -336,6 +336,10 @@ class BlockMatrix(DistributedMatrix):
         owners = {(i, j): c_owner[i * n + j] for i in range(m) for j in range(n)}
         return BlockMatrix(result, M, N, m, n, placement=lambda r, c, o=owners: o[(r, c)])
 
+    def inverse(self) -> "BlockMatrix":
+        """inverse() :527-531 — toDenseVecMatrix().inverse()"""
+        return self.toDenseVecMatrix().inverse()
+
     def _local_dtype(self):
         for _, s in self.blocks:
             return s.buf.dtype

@@ -22,6 +22,10 @@ from .distributed_matrix import DistributedMatrix
 from .sub_matrix import SubMatrix
 
 
+# the SparkConf keys the reference reads for its block algorithms (matrix/DenseVecMatrix.scala:313,499,591)
+conf: Dict[str, int] = {"marlin.lu.basesize": 1000, "marlin.cholesky.basesize": 1000, "marlin.inverse.basesize": 1000}
+
+
 def _ceil_len(total: int, parts: int) -> int:
     return int(math.ceil(float(total) / float(parts)))
 
@@ -209,6 +213,67 @@ class DenseVecMatrix(DistributedMatrix):
         cshard = SubMatrix(buf=cbuf, rows=nloc, cols=b_cols, ld=max(1, b_cols), is_transpose=True)
         self.data.multiply(Bd, out=cshard)
         return DenseVecMatrix(ids=self.ids, data=cshard, nRows=0, nCols=b_cols)
+
+    # ------------------------------------------------------------------ LU / Cholesky / inverse (:271-764)
+    def _square_blocks(self, base: int):
+        """All blocks of the ceil(n / base)^2 grid as device blocks on THIS rank (every rank factorises a replica)."""
+        from . import factorizations as fz
+        n = self.numRows()
+        nb, sub = fz.grid(n, base)
+        host = self.toBreeze()
+        rt = Runtime.get()
+        blocks = {(r, c): SubMatrix(host[r * sub:min(n, (r + 1) * sub), c * sub:min(n, (c + 1) * sub)], device=rt.device)
+                  for r in range(nb) for c in range(nb)}
+        return blocks, nb, sub, n
+
+    def _finish(self, blocks, nb: int, n: int):
+        from . import factorizations as fz
+        from .block_matrix import BlockMatrix
+        rank, ws = world()
+        owner = lambda r, c: comm.elem_owner(r, c, nb, ws)
+        return BlockMatrix(fz.block_pairs(blocks, owner, rank), n, n, nb, nb)
+
+    def luDecompose(self, mode: str = "auto", baseSize: Optional[int] = None, keepUnfactoredDiagonal: bool = False):
+        """luDecompose(mode) :283-466 -> (BlockMatrix holding L (unit lower) and U packed, permutation array: row i of
+        L*U is row perm[i] of this matrix).  Deviation, on purpose: the reference stores the ORIGINAL diagonal block for
+        every block row but the last (`scatterRdds(i)(0) = matFirst.cache()`, :355), which makes P A = L U false;
+        `keepUnfactoredDiagonal=True` reproduces that, the default stores the factors."""
+        from . import factorizations as fz
+        if self.numRows() != self.numCols():
+            raise nat.MarlinArgumentError(nat.MB_ERR_DIM_MISMATCH, f"LU decompose only support square matrix: {self.numRows()} v.s {self.numCols()}")
+        n = self.numRows()
+        if not fz.mode_is_dist(mode, n):
+            blocks, _, _, _ = self._square_blocks(n)
+            packed, perm = blocks[(0, 0)].lu()
+            return self._finish({(0, 0): packed}, 1, n), [int(p) for p in perm]
+        blocks, nb, sub, n = self._square_blocks(baseSize or conf.get("marlin.lu.basesize", 1000))
+        out, p_array = fz.lu_blocks(blocks, nb, sub, n, keepUnfactoredDiagonal)
+        return self._finish(out, nb, n), p_array
+
+    def choleskyDecompose(self, mode: str = "auto", baseSize: Optional[int] = None):
+        """choleskyDecompose(mode) :475-561 -> BlockMatrix of the lower-triangular blocks of L, L L^T = this (no blocks
+        above the diagonal, as in the reference; dims are set explicitly where the reference leaves them to be inferred)."""
+        from . import factorizations as fz
+        if self.numRows() != self.numCols():
+            raise nat.MarlinArgumentError(nat.MB_ERR_DIM_MISMATCH, f"LU decompose only support square matrix: {self.numRows()} v.s {self.numCols()}")
+        n = self.numRows()
+        if not fz.mode_is_dist(mode, n):
+            blocks, _, _, _ = self._square_blocks(n)
+            return self._finish({(0, 0): blocks[(0, 0)].cholesky()}, 1, n)
+        blocks, nb, _, n = self._square_blocks(baseSize or conf.get("marlin.cholesky.basesize", 1000))
+        return self._finish(fz.cholesky_blocks({k: v for k, v in blocks.items() if k[0] >= k[1]}, nb), nb, n)
+
+    def inverse(self, mode: str = "auto", baseSize: Optional[int] = None):
+        """inverse() :271-273, inverse(mode) :568-764"""
+        from . import factorizations as fz
+        if self.numRows() != self.numCols():
+            raise nat.MarlinArgumentError(nat.MB_ERR_DIM_MISMATCH, f"Inversion only support square matrix: {self.numRows()} v.s {self.numCols()}")
+        n = self.numRows()
+        if not fz.mode_is_dist(mode, n):
+            blocks, _, _, _ = self._square_blocks(n)
+            return self._finish({(0, 0): blocks[(0, 0)].inverse()}, 1, n)
+        blocks, nb, _, n = self._square_blocks(baseSize or conf.get("marlin.inverse.basesize", 1000))
+        return self._finish(fz.inverse_blocks(blocks, nb), nb, n)
 
     # ------------------------------------------------------------------ element-wise (:771-871)
     def _scalar(self, op: str, b: float) -> "DenseVecMatrix":

@@ -682,6 +682,145 @@ class DenseVecMatrix:
             return self.multiply_split(other, (s, s, s), gemm)
         return self.multiply_split(other, split_method(self.num_rows(), self.num_cols(), other.num_cols(), cores), gemm)
 
+    # ---- factorizations (matrix/DenseVecMatrix.scala:283-764).  Breeze's brzLU / brzCholesky / brzInv / `\` are LAPACK
+    #      calls (dgetrf, dpotrf, dgetrf+dgetri, dgesv); scipy / numpy call the same routines and stand in for them. ----
+    @staticmethod
+    def _mode_is_dist(mode: str, n: int) -> bool:
+        """:284-299 — "auto": distributed above 6000 rows, else local Breeze."""
+        if mode == "auto":
+            return n > 6000
+        if mode == "breeze":
+            return False
+        if mode == "dist":
+            return True
+        raise ValueError(f"Do not support mode {mode}.")
+
+    @staticmethod
+    def _perm_from_ipiv(ipiv) -> list:
+        """:303-308 — pArray: apply LAPACK's interchanges (0-based here) to 0..n-1."""
+        p = list(range(len(ipiv)))
+        for i, q in enumerate(ipiv):
+            p[i], p[q] = p[q], p[i]
+        return p
+
+    def lu_decompose(self, mode: str = "auto", base: int = 1000, keep_unfactored_diagonal: bool = True):
+        """luDecompose :283-466 -> (BlockMatrix with L (unit lower) and U packed, permutation array).
+        keep_unfactored_diagonal reproduces the reference as written: for every diagonal block except the last the
+        result holds the ORIGINAL block (`scatterRdds(i)(0) = matFirst.cache()`, :355) instead of its factors."""
+        import scipy.linalg as sla
+        n = self.num_rows()
+        if n != self.num_cols():
+            raise ValueError(f"LU decompose only support square matrix: {n} v.s {self.num_cols()}")
+        if not self._mode_is_dist(mode, n):
+            lu, piv = sla.lu_factor(self.to_breeze())
+            return BlockMatrix([((0, 0), lu)], n, n, 1, 1), self._perm_from_ipiv(piv)
+        nb = int(math.ceil(n / float(base)))
+        sub = int(math.ceil(n / float(nb)))
+        cur = dict(self.to_block_matrix(nb, nb).blocks)
+        p_array = [0] * n
+        scatter = {}
+        for i in range(nb):
+            first = cur[(i, i)]
+            mat, piv = sla.lu_factor(first)
+            perm = self._perm_from_ipiv(piv)
+            for j, pj in enumerate(perm):
+                p_array[i * sub + j] = i * sub + pj
+            if i == nb - 1:
+                cur = {(i, i): mat}
+                continue
+            second = {k: v for k, v in cur.items() if k[0] == i and k[1] > i}
+            third = {k: v for k, v in cur.items() if k[0] > i and k[1] == i}
+            forth = {k: v for k, v in cur.items() if k[0] > i and k[1] > i}
+            l = np.tril(mat, -1) + np.eye(mat.shape[0])
+            u = np.triu(mat)
+            pm = np.zeros((len(perm), len(perm)))
+            for j, pj in enumerate(perm):
+                pm[j, pj] = 1.0
+            scatter[(i, 0)] = {(i, i): first if keep_unfactored_diagonal else mat}
+            scatter[(i, 1)] = {k: np.linalg.solve(l, pm) @ v for k, v in second.items()}          # (l \ permutation) * block
+            scatter[(i, 2)] = {k: v @ np.linalg.inv(u) for k, v in third.items()}                  # block * brzInv(u)
+            mult = {(r, c): third[(r, i)] @ np.linalg.solve(first, second[(i, c)]) for (r, c) in forth}   # blk1 * (bdata \ blk2)
+            cur = {k: forth[k] - mult[k] for k in forth}
+        for part in scatter.values():
+            cur.update(part)
+        out = []
+        for (r, c), blk in cur.items():
+            if r > c:                                       # :440-455 — rows of a block below the diagonal follow its block row's pivots
+                arr = p_array[sub * r: (n if r == nb - 1 else sub * r + sub)]
+                pm = np.zeros((len(arr), len(arr)))
+                for j, a in enumerate(arr):
+                    pm[j, a - sub * r] = 1.0
+                blk = pm @ blk
+            out.append(((r, c), blk))
+        return BlockMatrix(out, n, n, nb, nb), p_array
+
+    def cholesky_decompose(self, mode: str = "auto", base: int = 1000) -> BlockMatrix:
+        """choleskyDecompose :475-561 -> lower-triangular blocks of L with L L^T = this (blocks above the diagonal are
+        absent from the result, as in the reference).  The reference builds the result with `new BlockMatrix(blkMat)`,
+        whose lazily derived numCols / numBlksByCol would then see one block in block-row 0; dims are given here."""
+        n = self.num_rows()
+        if n != self.num_cols():
+            raise ValueError(f"LU decompose only support square matrix: {n} v.s {self.num_cols()}")
+        if not self._mode_is_dist(mode, n):
+            return BlockMatrix([((0, 0), np.linalg.cholesky(self.to_breeze()))], n, n, 1, 1)
+        nb = int(math.ceil(n / float(base)))
+        cur = dict(self.to_block_matrix(nb, nb).blocks)
+        scatter = {}
+        for i in range(nb):
+            if i == nb - 1:
+                cur = {k: np.linalg.cholesky(v) for k, v in cur.items()}
+                continue
+            third = {k: v for k, v in cur.items() if k[0] > i and k[1] == i}
+            forth = {k: v for k, v in cur.items() if k[1] > i and k[0] >= k[1]}
+            mat = cur[(i, i)].copy()
+            for j in range(mat.shape[0]):                   # :521-523 — the lower triangle is overwritten from the upper one
+                for kk in range(j):
+                    mat[j, kk] = mat[kk, j]
+            l = np.linalg.cholesky(mat)
+            lt_inv = np.linalg.inv(l.T)
+            scatter[(i, 0)] = {(i, i): l}
+            scatter[(i, 1)] = {k: v @ lt_inv for k, v in third.items()}
+            mult = {(r, c): scatter[(i, 1)][(r, i)] @ scatter[(i, 1)][(c, i)].T for (r, c) in forth}
+            cur = {k: forth[k] - mult[k] for k in forth}
+        for part in scatter.values():
+            cur.update(part)
+        return BlockMatrix(list(cur.items()), n, n, nb, nb)
+
+    def inverse(self, mode: str = "auto", base: int = 1000) -> BlockMatrix:
+        """inverse :568-764 — local: brzInv; distributed: block elimination (inverse of the diagonal block, scaled row and
+        column panels, Schur complement), then the back substitution that assembles the inverse from the last block up."""
+        n = self.num_rows()
+        if n != self.num_cols():
+            raise ValueError(f"Inversion only support square matrix: {n} v.s {self.num_cols()}")
+        if not self._mode_is_dist(mode, n):
+            return BlockMatrix([((0, 0), np.linalg.inv(self.to_breeze()))], n, n, 1, 1)
+        nb = int(math.ceil(n / float(base)))
+        cur = dict(self.to_block_matrix(nb, nb).blocks)
+        sc = {}
+        for i in range(nb):
+            if i == nb - 1:
+                cur = {k: np.linalg.inv(v) for k, v in cur.items()}
+                continue
+            second = {k: v for k, v in cur.items() if k[0] == i and k[1] > i}
+            third = {k: v for k, v in cur.items() if k[0] > i and k[1] == i}
+            forth = {k: v for k, v in cur.items() if k[0] > i and k[1] > i}
+            inv = np.linalg.inv(cur[(i, i)])
+            sc[(i, 0)] = {(i, i): inv}
+            sc[(i, 1)] = {k: -inv @ v for k, v in second.items()}
+            sc[(i, 2)] = {k: -v @ inv for k, v in third.items()}
+            mult = {(r, c): (third[(r, i)] @ inv) @ second[(i, c)] for (r, c) in forth}
+            cur = {k: forth[k] - mult[k] for k in forth}
+        for i in range(nb - 2, -1, -1):
+            second_mat, third_mat = sc[(i, 1)], sc[(i, 2)]
+            rng_ = range(i + 1, nb)
+            mult_third = {(r, i): sum(cur[(r, c)] @ third_mat[(c, i)] for c in rng_) for r in rng_}        # :690-716
+            mult_second = {(i, c): sum(second_mat[(i, r)] @ cur[(r, c)] for r in rng_) for c in rng_}       # :718-742
+            first = sum(second_mat[(i, c)] @ mult_third[(c, i)] for c in rng_) + sc[(i, 0)][(i, i)]         # :744-754
+            cur.update(mult_second)
+            cur.update(mult_third)
+            cur[(i, i)] = first
+        return BlockMatrix(list(cur.items()), n, n, nb, nb)
+
     def add(self, other, subtract: bool = False) -> "DenseVecMatrix":
         """add :771-788 / subtract :795-810 — rows.join(that.rows), v1 + v2"""
         if isinstance(other, BlockMatrix):

@@ -280,3 +280,56 @@ def test_example_drivers(M, capsys):
     RMMcompare.main(["256", "256", "256", "2", "2", "2", "2"])
     out = capsys.readouterr().out
     assert "Result RDD counts" in out and "mode 3 used time" in out and "RMMv2 in mode 2 used time" in out
+
+
+# ------------------------------------------------------------------ LU / Cholesky / inverse
+def test_inverse_suite_case(M):                  # DistributedMatrixSuite.scala:340-352
+    rows = [(0, np.array([0.0, 0.0, 1.0])), (1, np.array([0.0, 1.0, 0.0])), (2, np.array([1.0, 0.0, 0.0]))]
+    inv = M.DenseVecMatrix(rows).inverse()
+    assert isinstance(inv, M.BlockMatrix)
+    assert np.array_equal(inv.toBreeze(), np.array([[0.0, 0.0, 1.0], [0.0, 1.0, 0.0], [1.0, 0.0, 0.0]]))
+
+
+@pytest.mark.parametrize("mode,base", [("breeze", None), ("dist", 7), ("dist", 40), ("auto", None)])
+def test_lu_cholesky_inverse_against_the_restated_reference(M, oracle, mode, base):
+    """The three block algorithms against the oracle's restatement of matrix/DenseVecMatrix.scala:283-764 (LAPACK through
+    scipy for the Breeze calls), both in "breeze" mode and in "dist" mode with small base sizes (ragged last block), to
+    1e-10 relative; plus the defining properties P A = L U, L L^T = A, A A^-1 = I."""
+    n = 93
+    rng = np.random.default_rng(7)
+    A = rng.random((n, n)) - 0.5 + 3.0 * np.eye(n)
+    rows = list(enumerate(A))
+    g, o = M.DenseVecMatrix(rows), oracle.DenseVecMatrix(rows)
+    kw = {} if base is None else {"baseSize": base}
+    okw = {} if base is None else {"base": base}
+    lu, perm = g.luDecompose(mode, **kw)
+    olu, operm = o.lu_decompose(mode, keep_unfactored_diagonal=False, **okw)
+    assert list(perm) == list(operm)
+    got = lu.toBreeze()
+    assert np.abs(got - olu.to_breeze()).max() <= 1e-10 * np.abs(got).max()
+    L, U = np.tril(got, -1) + np.eye(n), np.triu(got)
+    assert np.abs(A[perm] - L @ U).max() <= 1e-12
+    if mode == "dist":                           # the reference as written keeps the unfactored diagonal blocks (:355)
+        q, _ = g.luDecompose(mode, keepUnfactoredDiagonal=True, **kw)
+        oq, _ = o.lu_decompose(mode, keep_unfactored_diagonal=True, **okw)
+        assert np.abs(q.toBreeze() - oq.to_breeze()).max() <= 1e-10 * np.abs(got).max()
+    inv = g.inverse(mode, **kw).toBreeze()
+    assert np.abs(inv - o.inverse(mode, **okw).to_breeze()).max() <= 1e-10 * np.abs(inv).max()
+    assert np.abs(inv @ A - np.eye(n)).max() <= 1e-12
+    S = A @ A.T
+    srows = list(enumerate(S))
+    Lc = M.DenseVecMatrix(srows).choleskyDecompose(mode, **kw).toBreeze()
+    assert np.abs(Lc - oracle.DenseVecMatrix(srows).cholesky_decompose(mode, **okw).to_breeze()).max() <= 1e-10 * np.abs(Lc).max()
+    assert np.array_equal(np.triu(Lc, 1), np.zeros((n, n))) and np.abs(Lc @ Lc.T - S).max() <= 1e-11 * np.abs(S).max()
+
+
+def test_factorization_argument_errors(M):
+    d = M.DenseVecMatrix([(0, np.array([1.0, 2.0, 3.0])), (1, np.array([4.0, 5.0, 6.0]))])
+    for f in (d.luDecompose, d.choleskyDecompose, d.inverse):
+        with pytest.raises(ValueError):
+            f()
+    sq = M.DenseVecMatrix([(0, np.array([2.0, 0.0])), (1, np.array([0.0, 2.0]))])
+    with pytest.raises(ValueError):
+        sq.inverse("spark")
+    assert np.array_equal(M.BlockMatrix([(M.BlockID(0, 0), M.SubMatrix(np.array([[2.0, 0.0], [0.0, 4.0]])))]).inverse().toBreeze(),
+                          np.array([[0.5, 0.0], [0.0, 0.25]]))
