@@ -323,6 +323,11 @@ def test_fill_uniform_many_ctas_and_far_offsets(gpu, oracle, row_major):
         stream = oracle.uniform_stream_far(seed, first, rows * cols)      # independent GF(2) matrix power, then sequential
         ref = stream.reshape(rows, cols) if row_major else stream.reshape((rows, cols), order="F")
         assert np.array_equal(download(gpu, h, rows, cols), ref)
+    # a non-unit range on full CTAs (the fast kernel's affine path: two roundings, a + (b - a) * x as on the JVM)
+    nat.check(lib.mb_fill_uniform(ctx, h, 77, 5, -2.0, 5.0, row_major))
+    stream = oracle.uniform_stream(77, 5, rows * cols, -2.0, 5.0)
+    ref = stream.reshape(rows, cols) if row_major else stream.reshape((rows, cols), order="F")
+    assert np.array_equal(download(gpu, h, rows, cols), ref)
     big = alloc(gpu, rows + 9, cols + 5)
     nat.check(lib.mb_block_fill(ctx, big, -1.0))
     view = nat.c_blk()
