@@ -579,9 +579,39 @@ int32_t mb_matmul_blocked_subset(mb_ctx* ctx, mb_block* const* A_tiles, mb_block
             Ap[kk] = elem_ptr(a); Bp[kk] = elem_ptr(b); la[kk] = a->ld; lb[kk] = b->ld; Ks[kk] = a->cols;
         }
         if (seg_ok) {
+            // The tensor cores add into the fp32 TMEM accumulator with truncation, so one accumulation chain drifts by about
+            // (chain length in K) * 5e-9 relative on same-sign data (measured: 3.5e-4 at K = 65536).  Chains are therefore
+            // capped (MARLIN_B200_BF16_KCHAIN, default 8192; 0 = unlimited): an fp32 C block is produced by several
+            // launches whose epilogues add into C with round-to-nearest.  bf16 C blocks keep the single launch (one rounding).
+            static const long long kchain = [] { const char* e = getenv("MARLIN_B200_BF16_KCHAIN"); return e ? atoll(e) : 8192ll; }();
+            long long total_k = 0;
+            for (int kk = 0; kk < k; ++kk) total_k += Ks[kk];
             int launches = 0;
-            cudaError_t e = mb::gemm_bf16_segments(false, false, cb->rows, cb->cols, k, Ks, Ap, la, Bp, lb, elem_ptr(cb), cb->ld,
-                                                   cb->dtype == MB_F32, false, ctx->num_sms, ctx->stream, &launches);
+            cudaError_t e = cudaSuccess;
+            if (cb->dtype != MB_F32 || kchain <= 0 || total_k <= kchain) {
+                e = mb::gemm_bf16_segments(false, false, cb->rows, cb->cols, k, Ks, Ap, la, Bp, lb, elem_ptr(cb), cb->ld,
+                                           cb->dtype == MB_F32, false, ctx->num_sms, ctx->stream, &launches);
+            } else {
+                const void* sa[8]; const void* sb[8]; long long sla[8], slb[8]; int sk[8];
+                int ns = 0, group = 0;
+                long long in_group = 0;
+                auto flush = [&]() {
+                    if (ns == 0 || e != cudaSuccess) return;
+                    e = mb::gemm_bf16_segments(false, false, cb->rows, cb->cols, ns, sk, sa, sla, sb, slb, elem_ptr(cb), cb->ld, true,
+                                               group > 0, ctx->num_sms, ctx->stream, &launches);
+                    ++group; ns = 0; in_group = 0;
+                };
+                for (int kk = 0; kk < k && e == cudaSuccess; ++kk)
+                    for (int k0 = 0; k0 < Ks[kk] && e == cudaSuccess;) {
+                        const int len = (int)std::min<long long>(Ks[kk] - k0, kchain - in_group);
+                        sa[ns] = static_cast<const char*>(Ap[kk]) + (size_t)k0 * la[kk] * 2;       // columns k0.. of A(i,kk)
+                        sb[ns] = static_cast<const char*>(Bp[kk]) + (size_t)k0 * 2;                // rows k0.. of B(kk,j)
+                        sla[ns] = la[kk]; slb[ns] = lb[kk]; sk[ns] = len;
+                        ++ns; in_group += len; k0 += len;
+                        if (in_group >= kchain || ns == 8) flush();
+                    }
+                flush();
+            }
             if (e == cudaSuccess) { ctx->launches += launches; continue; }
             if (e != cudaErrorNotSupported) return cuda_fail(e, "gemm_bf16_segments");
             cudaGetLastError();
