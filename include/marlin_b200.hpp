@@ -154,6 +154,21 @@ public:
         check(mb_block_ger(Context::get(), h_.get(), o.h_.get(), r.h_.get()));
         return r;
     }
+    // brzLU / brzCholesky / brzInv of DenseVecMatrix.luDecompose / choleskyDecompose / inverse (DenseVecMatrix.scala:302,495,587)
+    SubMatrix copy() const { SubMatrix r = empty(rows(), cols()); check(mb_block_copy(Context::get(), h_.get(), r.h_.get())); return r; }
+    std::pair<SubMatrix, std::vector<int>> lu() const {
+        SubMatrix r = copy();
+        std::vector<int32_t> perm((size_t)std::max(1, rows()));
+        check(mb_block_lu(Context::get(), r.h_.get(), perm.data()));
+        return {r, std::vector<int>(perm.begin(), perm.begin() + rows())};
+    }
+    SubMatrix cholesky() const { SubMatrix r = copy(); check(mb_block_cholesky(Context::get(), r.h_.get())); return r; }
+    SubMatrix inverse() const { SubMatrix r = empty(rows(), cols()); check(mb_block_inverse(Context::get(), h_.get(), r.h_.get())); return r; }
+    SubMatrix solveTriangular(const SubMatrix& rhs, bool lower, bool unit = false) const {      // this \ rhs
+        SubMatrix x = rhs.copy();
+        check(mb_block_trsm(Context::get(), h_.get(), lower ? 1 : 0, unit ? 1 : 0, x.h_.get()));
+        return x;
+    }
     void assign(const SubMatrix& src) { check(mb_block_copy(Context::get(), src.h_.get(), h_.get())); }   // this(range) := src
     double sum() const { double s = 0; check(mb_block_sum(Context::get(), h_.get(), &s)); return s; }
     DenseMatrix denseBlock() const {                                                  // collect to the host (toBreeze)
@@ -567,6 +582,40 @@ public:
                 for (int i = 0; i < m; ++i) out.emplace_back(BlockID(i, kv.first.column, i * n * k + kv.first.column * k + kv.first.row), kv.second);
         }
         return out;
+    }
+
+    // ---- luDecompose / choleskyDecompose / inverse, "breeze" mode (:300-309, :494-497, :585-589): the matrix is one block on
+    //      the device and the factorization one library call.  The distributed block algorithms (:310-466, :497-556,
+    //      :589-760) live in the Python mirror (marlin_b200/matrix/factorizations.py) on the same block kernels.
+    static bool modeIsDist(const std::string& mode, long n) {
+        if (mode == "auto") return n > 6000;
+        if (mode == "breeze") return false;
+        if (mode == "dist") return true;
+        throw std::invalid_argument("Do not support mode " + mode + ".");
+    }
+    SubMatrix asOneBlock() {                                                          // toBreeze() as a device block, rows in id order
+        const int n = (int)numRows(), cols = (int)numCols();
+        SubMatrix fullT = SubMatrix::empty(cols, n);
+        check(mb_block_fill(Context::get(), fullT.handle(), 0.0));
+        SubMatrix full = fullT.t();
+        for (size_t p = 0; p < ids_.size(); ++p) full.slice((int)ids_[p], (int)ids_[p] + 1, 0, cols).assign(data_.slice((int)p, (int)p + 1, 0, cols));
+        return full.copy();
+    }
+    std::pair<BlockMatrix, std::vector<int>> luDecompose(const std::string& mode = "auto") {
+        if (numRows() != numCols()) throw std::invalid_argument("LU decompose only support square matrix: " + std::to_string(numRows()) + " v.s " + std::to_string(numCols()));
+        if (modeIsDist(mode, numRows())) throw std::invalid_argument("the C++ mirror runs the local (breeze) mode; use the Python host for mode dist");
+        auto res = asOneBlock().lu();
+        return {BlockMatrix({{BlockID(0, 0), res.first}}, numRows(), numCols(), 1, 1), res.second};
+    }
+    BlockMatrix choleskyDecompose(const std::string& mode = "auto") {
+        if (numRows() != numCols()) throw std::invalid_argument("LU decompose only support square matrix: " + std::to_string(numRows()) + " v.s " + std::to_string(numCols()));
+        if (modeIsDist(mode, numRows())) throw std::invalid_argument("the C++ mirror runs the local (breeze) mode; use the Python host for mode dist");
+        return BlockMatrix({{BlockID(0, 0), asOneBlock().cholesky()}}, numRows(), numCols(), 1, 1);
+    }
+    BlockMatrix inverse(const std::string& mode = "auto") {
+        if (numRows() != numCols()) throw std::invalid_argument("Inversion only support square matrix: " + std::to_string(numRows()) + " v.s " + std::to_string(numCols()));
+        if (modeIsDist(mode, numRows())) throw std::invalid_argument("the C++ mirror runs the local (breeze) mode; use the Python host for mode dist");
+        return BlockMatrix({{BlockID(0, 0), asOneBlock().inverse()}}, numRows(), numCols(), 1, 1);
     }
 
 private:

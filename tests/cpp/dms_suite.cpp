@@ -171,6 +171,20 @@ int main() {
         CHECK(mat.dotProduct(blkMat).toBreeze() == dot);
         CHECK(blkMat.dotProduct(blkMat).toBreeze() == dot);
     });
+    test("DenseVecMatrix inverse", [&] {                                           // :340-352
+        DenseVecMatrix mat({{0, {0.0, 0.0, 1.0}}, {1, {0.0, 1.0, 0.0}}, {2, {1.0, 0.0, 0.0}}});
+        BlockMatrix inv = mat.inverse();
+        CHECK(inv.toBreeze() == (BDM{{0.0, 0.0, 1.0}, {0.0, 1.0, 0.0}, {1.0, 0.0, 0.0}}));
+        // LU and Cholesky of small exact cases: P A = L U with integer factors, L L^T = A
+        DenseVecMatrix a({{0, {2.0, 1.0}}, {1, {4.0, 5.0}}});
+        auto lu = a.luDecompose("breeze");
+        CHECK(lu.second == (std::vector<int>{1, 0}));                             // pivot: |4| > |2|
+        CHECK(lu.first.toBreeze() == (BDM{{4.0, 5.0}, {0.5, -1.5}}));
+        DenseVecMatrix spd({{0, {4.0, 2.0}}, {1, {2.0, 10.0}}});
+        CHECK(spd.choleskyDecompose().toBreeze() == (BDM{{2.0, 0.0}, {1.0, 3.0}}));
+        CHECK((throws<std::invalid_argument>([&] { DenseVecMatrix r({{0, {1.0, 2.0, 3.0}}}); r.inverse(); })));
+    });
+
     test("BlockMatrix to BlockMatrix", [&] {                                      // :411-418
         DenseVecMatrix mat(data());
         BlockMatrix blk1 = mat.toBlockMatrix(2, 2);
