@@ -104,6 +104,39 @@ for n in (() if "hbm" in sys.argv[1:] else (4096, 8192, 16384)):
                       "frac_of_measured_bf16_peak": fl / ms32 / 1e9 / BF16}
     del A, B, Cm, C16, ta, tb, tc
 out["bf16_gemm"] = gemm
+
+# ---- f1: layout conversion on the device (rows -> blocks -> rows), 2 * 8 * M * N bytes per direction ----
+f1 = {}
+for (M_, N_, gr, gc) in (() if "hbm" in sys.argv[1:] else ((16384, 16384, 2, 2), (1048576, 1024, 8, 1))):
+    D = mb.MTUtils.randomDenVecMatrix(None, M_, N_, numPartitions=1, seed=5)
+    torch.cuda.synchronize()
+    Bm = D.toBlockMatrix(gr, gc)
+    ms_rb = timeit(lambda: D.toBlockMatrix(gr, gc), 5, 2)
+    ms_br = timeit(lambda: Bm.toDenseVecMatrix(), 5, 2)
+    ms_rg = timeit(lambda: Bm.toBlockMatrix(gr * 2, gc), 5, 2)
+    by = 16.0 * M_ * N_
+    f1[f"{M_}x{N_} fp64, {gr}x{gc} grid"] = {
+        "rows_to_blocks": {"ms": ms_rb, "GB/s": by / ms_rb / 1e6, "frac_of_measured_hbm": by / ms_rb / 1e6 / HBM},
+        "blocks_to_rows": {"ms": ms_br, "GB/s": by / ms_br / 1e6, "frac_of_measured_hbm": by / ms_br / 1e6 / HBM},
+        "regrid": {"ms": ms_rg, "GB/s": by / ms_rg / 1e6, "frac_of_measured_hbm": by / ms_rg / 1e6 / HBM}}
+    del D, Bm
+    torch.cuda.empty_cache()
+out["f1_layout_conversion"] = f1
+
+# ---- f4: factorizations of one block (recursive; the flops run in the DMMA GEMM) ----
+fac = {}
+for n in (() if "hbm" in sys.argv[1:] else (4096, 8192)):
+    A = mb.MTUtils.randomBlockMatrix(None, n, n, 1, 1, seed=6).blocks[0][1]
+    S = A.multiply(A.t)
+    S.add_(mb.SubMatrix(torch.eye(n, dtype=torch.float64).mul_(float(n)).numpy(), device=rt.device))
+    ms_lu = timeit(lambda: A.lu(), 3, 1)
+    ms_ch = timeit(lambda: S.cholesky(), 3, 1)
+    ms_inv = timeit(lambda: S.inverse(), 3, 1)
+    fac[f"{n}^2"] = {"lu_ms": ms_lu, "lu_tflops": (2.0 / 3.0) * n ** 3 / ms_lu / 1e9, "cholesky_ms": ms_ch,
+                     "cholesky_tflops": (1.0 / 3.0) * n ** 3 / ms_ch / 1e9, "inverse_ms": ms_inv, "inverse_tflops": 2.0 * n ** 3 / ms_inv / 1e9,
+                     "note": "times include the working copy of the block and, for LU, the D2H of the pivots"}
+    del A, S
+out["f4_factorizations"] = fac
 Path("gpurun_out").mkdir(exist_ok=True)
 Path("gpurun_out/kernels.json").write_text(json.dumps(out, indent=1))
 print(json.dumps(out, indent=1))
