@@ -34,6 +34,7 @@ sys.path.insert(0, str(ROOT))
 # line); cpu_threads() re-applies it through threadpoolctl and reports the count OpenBLAS really uses.
 HOST_CORES = os.cpu_count() or 1
 os.environ["OPENBLAS_NUM_THREADS"] = str(HOST_CORES)
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")     # one hardware queue per stream (see marlin_b200/__init__.py)
 
 FP64_PEAK_TFLOPS_MEASURED = 37.1   # scripts/dmma_bench.cu on this pool's B200 (profiles/r01_probe_*): 148 SM x 64 DFMA/clk x 1.965 GHz
 METRIC = "fp64 dense multiply throughput (2*N^3 flop), 16384x16384 BlockMatrix 2x2 grid"

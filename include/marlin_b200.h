@@ -256,7 +256,10 @@ int32_t mb_memcpy_async(mb_ctx* ctx, void* dst, const void* src, int64_t bytes);
  * Every rank calls it with the same m, k, n, lengths and owner maps; A_tiles[i*k+kk] / B_tiles[kk*n+j] are non-NULL
  * exactly where the owner map names this rank; C_tiles[i*n+j] must be a preallocated (row_len[i] x col_len[j]) block
  * (F64, or F32 for BF16 inputs) wherever mb_dist_plan's c_owner names this rank, and receives the finished tile there.
- * Asynchronous like every other compute entry: ordered on the ctx stream. */
+ * Asynchronous like every other compute entry: ordered on the ctx stream.  Flags between the processes are stream memory
+ * operations and peer stores, never kernels (nothing the resident GEMM waits for needs an SM); in-kernel waits are bounded
+ * by MARLIN_B200_TIMEOUT_S, host-side waits too (then the communicator aborts itself and the call returns MB_ERR_TIMEOUT).
+ * Give every stream its own hardware queue: CUDA_DEVICE_MAX_CONNECTIONS=32 before the CUDA context is created. */
 typedef struct mb_comm mb_comm;
 #define MB_ERR_TIMEOUT       -7   /* a peer did not answer within MARLIN_B200_TIMEOUT_S (default 120 s) -> RuntimeException */
 int32_t mb_comm_init(mb_ctx* ctx, int32_t rank, int32_t world, const char* session, mb_comm** out);
@@ -264,6 +267,7 @@ int32_t mb_comm_destroy(mb_comm* comm);
 int32_t mb_comm_rank(const mb_comm* comm);
 int32_t mb_comm_world(const mb_comm* comm);
 int32_t mb_comm_barrier(mb_comm* comm);            /* host-side barrier of the ranks */
+int32_t mb_comm_abort(mb_comm* comm);              /* release every wait queued on this rank (results garbage); the comm is dead */
 int32_t mb_comm_check(mb_comm* comm);              /* MB_ERR_TIMEOUT if a device-side wait for a peer ever gave up */
 /* MatrixMultPartitioner + placement: product seq -> rank (m*k*n entries) and C tile -> owning rank (m*n entries). */
 int32_t mb_dist_plan(int32_t m, int32_t k, int32_t n, int32_t world, int32_t* product_rank_out, int32_t* c_owner_out);

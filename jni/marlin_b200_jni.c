@@ -184,6 +184,7 @@ NATIVE(jlong, commInit)(JNIEnv* e, jobject o, jlong ctx, jint rank, jint world, 
 NATIVE(void, commDestroy)(JNIEnv* e, jobject o, jlong comm) { raise(e, mb_comm_destroy(COMM(comm))); }
 NATIVE(void, commBarrier)(JNIEnv* e, jobject o, jlong comm) { raise(e, mb_comm_barrier(COMM(comm))); }
 NATIVE(void, commCheck)(JNIEnv* e, jobject o, jlong comm) { raise(e, mb_comm_check(COMM(comm))); }
+NATIVE(void, commAbort)(JNIEnv* e, jobject o, jlong comm) { raise(e, mb_comm_abort(COMM(comm))); }
 NATIVE(jintArray, distPlan)(JNIEnv* e, jobject o, jint m, jint k, jint n, jint world) {
     /* returns m*k*n product ranks followed by m*n C-tile owners */
     const jsize np = m * k * n, nc = m * n;

@@ -104,6 +104,7 @@ SIGNATURES = {
     "mb_comm_world": (c_i32, [C.c_void_p]),
     "mb_comm_barrier": (c_i32, [C.c_void_p]),
     "mb_comm_check": (c_i32, [C.c_void_p]),
+    "mb_comm_abort": (c_i32, [C.c_void_p]),
     "mb_dist_plan": (c_i32, [c_i32, c_i32, c_i32, c_i32, C.POINTER(c_i32), C.POINTER(c_i32)]),
     "mb_dist_host_homes": (c_i32, [c_i32, c_i32, c_i32, c_i32, C.POINTER(c_i32), C.POINTER(c_i32)]),
     "mb_matmul_blocked_dist_host": (c_i32, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(c_i32), C.POINTER(C.c_void_p), C.POINTER(c_i32),

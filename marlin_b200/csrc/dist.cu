@@ -117,7 +117,12 @@ struct mb_comm {
     double timeout_s = 120.0;
     std::vector<cudaEvent_t> events;                 // pool, reused every call
     size_t events_used = 0;
+    bool aborted = false;                            // abort_local() ran: every later call fails
+    bool remote_write_ok = true;                     // cuStreamWriteValue64 accepted a peer address (else: 8-byte copies)
+    unsigned long long* ring = nullptr;              // pinned host values for the copy-based flag writes
+    size_t ring_pos = 0;
 };
+constexpr size_t RING_SLOTS = 8192;
 
 namespace {
 
@@ -153,13 +158,57 @@ int32_t spin_until(mb_comm* c, Pred p, const char* what) {
     return MB_OK;
 }
 
+// Flag writes and stream-side waits are STREAM MEMORY OPERATIONS (cuStreamWriteValue64 / cuStreamWaitValue64), executed
+// by the front end in stream order — never kernels: a kernel that becomes runnable while the persistent GEMM holds every
+// SM may not be scheduled until that GEMM retires (scripts/probe_copy_under_persistent.cu), and the GEMM may be waiting for
+// exactly that flag.  Copies (copy engines) and memory operations are the only things the resident GEMM ever waits for.
+// Writes to a peer's flag word fall back to an 8-byte copy if the driver refuses memory operations on peer addresses.
 cudaError_t sig(mb_comm* c, unsigned long long* flag, unsigned long long v, cudaStream_t st) {
-    c->ctx->launches++;
-    return mb::flag_signal(flag, v, st);
+    const bool local = flag >= c->flags && flag < c->flags + FLAG_WORDS;
+    if (local || c->remote_write_ok) {
+        cudaError_t e = mb::stream_write64(flag, v, st);
+        if (e == cudaSuccess || local) return e;
+        c->remote_write_ok = false;
+        cudaGetLastError();
+    }
+    unsigned long long* slot = c->ring + (c->ring_pos++ % RING_SLOTS);
+    *slot = v;
+    return cudaMemcpyAsync(flag, slot, 8, cudaMemcpyHostToDevice, st);
 }
+// Unbounded on the device (a memory operation cannot time out); a rank that loses its peers notices at the next host-side
+// rendezvous (bounded) and mb_comm_abort() releases whatever is still queued.
 cudaError_t waitf(mb_comm* c, const unsigned long long* flag, unsigned long long v, cudaStream_t st) {
-    c->ctx->launches++;
-    return mb::flag_wait_bounded(flag, v, timeout_ns(c), c->flags + F_STATUS, st);
+    (void)c;
+    return mb::stream_wait64_geq(flag, v, st);
+}
+// Release everything this rank still has queued behind flag waits: every local flag word jumps far ahead of any epoch
+// (the waits are cyclic >=), the streams drain with garbage results, the communicator is dead afterwards.
+void abort_local(mb_comm* c) {
+    if (c->aborted) return;
+    c->aborted = true;
+    cudaStream_t t = nullptr;
+    if (cudaStreamCreateWithFlags(&t, cudaStreamNonBlocking) != cudaSuccess) return;
+    std::vector<unsigned long long> big(FLAG_WORDS, 1ull << 62);
+    cudaMemcpyAsync(c->flags, big.data(), sizeof(unsigned long long) * FLAG_WORDS, cudaMemcpyHostToDevice, t);
+    cudaStreamSynchronize(t);
+    cudaStreamDestroy(t);
+}
+// cudaStreamSynchronize with a deadline: a peer that died leaves this rank's streams parked on a memory-operation wait
+// that no API call can cancel — so poll, and on timeout release the waits ourselves and report.
+int32_t sync_bounded(mb_comm* c, cudaStream_t st, const char* what) {
+    const double t0 = now_s();
+    for (int spins = 0;; ++spins) {
+        cudaError_t e = cudaStreamQuery(st);
+        if (e == cudaSuccess) return MB_OK;
+        if (e != cudaErrorNotReady) return cuda_fail(e, what);
+        if (spins > 200) usleep(50);
+        if (now_s() - t0 > c->timeout_s) {
+            abort_local(c);
+            cudaStreamSynchronize(st);
+            return fail(MB_ERR_TIMEOUT, "%s: no progress for %.0f s (a peer died or fell out of step); the communicator has been aborted", what,
+                        c->timeout_s);
+        }
+    }
 }
 cudaEvent_t next_event(mb_comm* c) {
     if (c->events_used == c->events.size()) {
@@ -331,7 +380,10 @@ int32_t mb_comm_init(mb_ctx* ctx, int32_t rank, int32_t world, const char* sessi
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_compute, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_tmp, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaMallocHost(&c->status_host, 8);
+    if (e == cudaSuccess) e = cudaMallocHost(&c->ring, RING_SLOTS * 8);
     if (e != cudaSuccess) return bail(cuda_fail(e, "mb_comm_init"));
+    if (!mb::stream_memops_available())
+        return bail(fail(MB_ERR_UNSUPPORTED, "mb_comm_init: the driver does not expose cuStreamWriteValue64 / cuStreamWaitValue64"));
     *c->status_host = 0;
     ShmRank& me = c->shm->r[rank];
     long long off = 0, bytes = 0;
@@ -350,6 +402,15 @@ int32_t mb_comm_init(mb_ctx* ctx, int32_t rank, int32_t world, const char* sessi
     }
     int32_t r = host_barrier(c);
     if (r) return bail(r);
+    // does the driver accept stream memory operations on peer addresses?  (one probe write per peer into a spare word)
+    for (int q = 0; q < world && c->remote_write_ok; ++q)
+        if (q != rank && mb::stream_write64(c->flags_peer[q] + F_STATUS + 1 + (rank % 4), 1, c->X) != cudaSuccess) {
+            c->remote_write_ok = false;
+            cudaGetLastError();
+        }
+    cudaStreamSynchronize(c->X);
+    if (cudaGetLastError() != cudaSuccess) c->remote_write_ok = false;
+    if ((r = host_barrier(c)) != MB_OK) return bail(r);
     if (rank == 0) shm_unlink(c->name.c_str());          // everyone has mapped it; the name can go
     *out = c;
     return MB_OK;
@@ -365,6 +426,7 @@ int32_t mb_comm_destroy(mb_comm* c) {
     if (c->arena) cudaFree(c->arena);
     if (c->flags) cudaFree(c->flags);
     if (c->status_host) cudaFreeHost(c->status_host);
+    if (c->ring) cudaFreeHost(c->ring);
     for (auto ev : c->events) cudaEventDestroy(ev);
     if (c->ev_compute) cudaEventDestroy(c->ev_compute);
     if (c->ev_tmp) cudaEventDestroy(c->ev_tmp);
@@ -382,12 +444,22 @@ int32_t mb_comm_barrier(mb_comm* c) {
     return host_barrier(c);
 }
 
+// Give up on the peers: releases every wait this rank has queued (results are garbage), later calls fail.
+int32_t mb_comm_abort(mb_comm* c) {
+    if (!c) return fail(MB_ERR_INVALID_ARG, "null communicator");
+    MB_CTX(c->ctx);
+    abort_local(c);
+    return MB_OK;
+}
+
 // Has any bounded device-side wait given up since the communicator was created?  (Synchronises the context stream.)
 int32_t mb_comm_check(mb_comm* c) {
     if (!c) return fail(MB_ERR_INVALID_ARG, "null communicator");
     MB_CTX(c->ctx);
+    if (c->aborted) return fail(MB_ERR_TIMEOUT, "mb_comm: the communicator was aborted after a peer stopped answering");
     MB_CUDA(cudaMemcpyAsync(c->status_host, c->flags + F_STATUS, 8, cudaMemcpyDeviceToHost, c->ctx->stream));
-    MB_CUDA(cudaStreamSynchronize(c->ctx->stream));
+    int32_t rs = sync_bounded(c, c->ctx->stream, "mb_comm_check");
+    if (rs) return rs;
     if (*c->status_host != 0)
         return fail(MB_ERR_TIMEOUT, "mb_comm: a device-side wait for a peer timed out (code %llu): a rank died or fell out of step; "
                     "results since then are invalid", *c->status_host);
@@ -408,6 +480,7 @@ int32_t mb_matmul_blocked_dist(mb_comm* c, mb_block* const* A_tiles, const int32
     MB_LOCK(ctx);
     if (!A_tiles || !B_tiles || !C_tiles || !a_owner || !b_owner || !row_len || !k_len || !col_len || m <= 0 || k <= 0 || n <= 0)
         return fail(MB_ERR_INVALID_ARG, "mb_matmul_blocked_dist: bad argument");
+    if (c->aborted) return fail(MB_ERR_TIMEOUT, "mb_comm: the communicator was aborted after a peer stopped answering");
     if (dtype != MB_F64 && dtype != MB_BF16) return fail(MB_ERR_UNSUPPORTED, "mb_matmul_blocked_dist: fp64 or bf16 tiles");
     const int rank = c->rank, world = c->world;
     const int out_dtype = dtype == MB_BF16 ? MB_F32 : MB_F64;
@@ -941,6 +1014,7 @@ int32_t mb_matmul_blocked_dist_host(mb_comm* c, const double* const* A_host, con
     MB_LOCK(ctx);
     if (!A_host || !B_host || !C_host || !a_home || !b_home || !row_len || !k_len || !col_len || m <= 0 || k <= 0 || n <= 0)
         return fail(MB_ERR_INVALID_ARG, "mb_matmul_blocked_dist_host: bad argument");
+    if (c->aborted) return fail(MB_ERR_TIMEOUT, "mb_comm: the communicator was aborted after a peer stopped answering");
     const int rank = c->rank, world = c->world;
     if (k > mb::G2_MAX_SEG) return fail(MB_ERR_UNSUPPORTED, "mb_matmul_blocked_dist_host: k = %d > %d", k, mb::G2_MAX_SEG);
     for (int i = 0; i < m; ++i) if (row_len[i] <= 0) return fail(MB_ERR_UNSUPPORTED, "mb_matmul_blocked_dist_host: empty block row");
@@ -1179,7 +1253,14 @@ int32_t mb_matmul_blocked_dist_host(mb_comm* c, const double* const* A_host, con
                 subs.push_back(sb);
             }
     }
-    std::stable_sort(subs.begin(), subs.end(), [](const Sub& a, const Sub& b) { return a.wave != b.wave ? a.wave < b.wave : (a.id != b.id ? a.id < b.id : (a.p != b.p ? a.p < b.p : a.q < b.q)); });
+    // wavefront order (the bands arrive in order); inside a wave the sub-blocks the PEER reduces come first, so that by the
+    // time this rank reaches its own sub-blocks of the wave the peer — which runs the mirror-image order — has stored its
+    // partials of them into this rank's staging buffer
+    std::stable_sort(subs.begin(), subs.end(), [](const Sub& a, const Sub& b) {
+        if (a.wave != b.wave) return a.wave < b.wave;
+        if (a.mine != b.mine) return !a.mine;
+        return a.id != b.id ? a.id < b.id : (a.p != b.p ? a.p < b.p : a.q < b.q);
+    });
     for (Sub& sb : subs) {
         const int i = sb.id / n, j = sb.id % n;
         const MyC* mc = nullptr;
@@ -1199,6 +1280,15 @@ int32_t mb_matmul_blocked_dist_host(mb_comm* c, const double* const* A_host, con
         if (sb.mine) {
             en.D = reinterpret_cast<double*>(c->arena + coff[sb.id]) + (size_t)sb.n_off * ldc + sb.m_off; en.ldd = ldc;
             en.sig_local = c->flags + F_SIG + sb.entry;
+            if (h.size() == 2) {
+                // reduce in the epilogue: my partial + the peer's staged partial (no separate add kernel: a kernel launched
+                // while this GEMM is resident might not be scheduled before it ends)
+                const int peer = h[0] == rank ? h[1] : h[0];
+                en.Cin = reinterpret_cast<const double*>(c->staging + (size_t)peer * c->slot_bytes + slot_off[sb.id]) + (size_t)sb.n_off * ldc + sb.m_off;
+                en.ldcin = ldc;
+                en.cin_flag = c->flags + F_SUBDONE + peer * SUB_SLOTS + sb.sub_idx;
+                en.cin_val = e;
+            }
         } else {
             const int peer = h[0] == rank ? h[1] : h[0];
             en.D = reinterpret_cast<double*>(c->staging_peer[peer] + (size_t)rank * c->slot_bytes + slot_off[sb.id]) + (size_t)sb.n_off * ldc + sb.m_off;
@@ -1218,26 +1308,19 @@ int32_t mb_matmul_blocked_dist_host(mb_comm* c, const double* const* A_host, con
     c->have_compute = true;
     for (int p = 0; p < world; ++p) if (writes_to[p]) c->last_write_epoch[p] = e;
 
-    // ---- reduce stream: finished sub-blocks -> (+ the peer's partial) -> host ----
+    // ---- download stream: finished (already reduced) sub-blocks -> host, hidden behind the rest of the GEMM ----
     for (const Sub& sb : subs) {
         if (!sb.mine) continue;
         const int i = sb.id / n;
         const int ldc = even(row_len[i]);
-        const auto& h = plan.holders[sb.id];
         MB_CUDA(waitf(c, c->flags + F_SIG + sb.entry, e, R));
-        double* mine_ptr = reinterpret_cast<double*>(c->arena + coff[sb.id]) + (size_t)sb.n_off * ldc + sb.m_off;
-        if (h.size() == 2) {
-            const int peer = h[0] == rank ? h[1] : h[0];
-            MB_CUDA(waitf(c, c->flags + F_SUBDONE + peer * SUB_SLOTS + sb.sub_idx, e, R));
-            const double* staged = reinterpret_cast<const double*>(c->staging + (size_t)peer * c->slot_bytes + slot_off[sb.id]) + (size_t)sb.n_off * ldc + sb.m_off;
-            MB_CUDA(mb::ew_binary(mb::EW_ADD, sb.M, sb.N, mine_ptr, 1, ldc, staged, 1, ldc, mine_ptr, 1, ldc, R));
-            ctx->launches++;
-        }
+        const double* mine_ptr = reinterpret_cast<const double*>(c->arena + coff[sb.id]) + (size_t)sb.n_off * ldc + sb.m_off;
         MB_CUDA(cudaMemcpy2DAsync(C_host[sb.id] + (size_t)sb.n_off * row_len[i] + sb.m_off, (size_t)row_len[i] * 8, mine_ptr, (size_t)ldc * 8,
                                   (size_t)sb.M * 8, sb.N, cudaMemcpyDeviceToHost, R));
     }
+    // the peer's staged partials have been consumed once my GEMM is done
     for (int p = 0; p < world; ++p)
-        if (reads_from[p]) MB_CUDA(sig(c, flag_ch(c, p, CH_FREE, rank), e, R));
+        if (reads_from[p]) MB_CUDA(sig(c, flag_ch(c, p, CH_FREE, rank), e, S));
     // ---- my upload buffers may not be overwritten until everyone has pulled them; S is ordered behind R ----
     for (int p = 0; p < world; ++p)
         if (consumer[p]) MB_CUDA(waitf(c, flag_ch(c, rank, CH_DONE, p), e, S));
@@ -1246,10 +1329,10 @@ int32_t mb_matmul_blocked_dist_host(mb_comm* c, const double* const* A_host, con
     MB_CUDA(cudaEventRecord(c->ev_tmp, U));
     MB_CUDA(cudaStreamWaitEvent(S, c->ev_tmp, 0));
     MB_CUDA(cudaMemcpyAsync(c->status_host, c->flags + F_STATUS, 8, cudaMemcpyDeviceToHost, S));
-    MB_CUDA(cudaStreamSynchronize(R));
-    MB_CUDA(cudaStreamSynchronize(S));
+    if ((rc = sync_bounded(c, R, "mb_matmul_blocked_dist_host")) != MB_OK) return rc;
+    if ((rc = sync_bounded(c, S, "mb_matmul_blocked_dist_host")) != MB_OK) return rc;
     if (*c->status_host != 0)
-        return fail(MB_ERR_TIMEOUT, "mb_matmul_blocked_dist_host: a device-side wait for a peer timed out (a rank died or fell out of step)");
+        return fail(MB_ERR_TIMEOUT, "mb_matmul_blocked_dist_host: a device-side wait for a peer timed out (status 0x%llx: a rank died or fell out of step)", *c->status_host);
     return MB_OK;
 }
 

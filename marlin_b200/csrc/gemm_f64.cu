@@ -318,14 +318,14 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
 // garbage, the host sees the status word and reports MB_ERR_TIMEOUT instead of hanging the GPU).
 template <bool SYS>
 __device__ __forceinline__ void wait_flag_ge(const unsigned long long* flag, unsigned long long v, long long timeout_ns,
-                                             unsigned long long* status) {
+                                             unsigned long long* status, unsigned long long tag = 1ull) {
     if ((SYS ? ld_acquire_sys(flag) : ld_acquire_gpu(flag)) >= v) return;
     const unsigned long long t0 = globaltimer_ns();
     for (unsigned spins = 0;; ++spins) {
         if ((SYS ? ld_acquire_sys(flag) : ld_acquire_gpu(flag)) >= v) return;
         __nanosleep(64);
         if ((spins & 255u) == 255u && timeout_ns > 0 && (long long)(globaltimer_ns() - t0) > timeout_ns) {
-            if (status) *status = 1ull;
+            if (status) *status = tag;
             return;
         }
     }
@@ -370,9 +370,11 @@ gemm_f64_dmma_grouped_kernel(const __grid_constant__ G2Params g) {
                     const int ia = en.a_op[sg], ib = en.b_op[sg];
                     // operand bands still in flight?  (pulled / uploaded tiles only; resident tiles have ready = -1)
                     if (g.a_ready[ia] >= 0)
-                        wait_flag_ge<false>(g.ready + g.a_ready[ia] + m0 / g.a_band[ia], g.ready_val, g.timeout_ns, g.status);
+                        wait_flag_ge<false>(g.ready + g.a_ready[ia] + m0 / g.a_band[ia], g.ready_val, g.timeout_ns, g.status,
+                                            (1ull << 56) | (1ull << 48) | (unsigned long long)(g.a_ready[ia] + m0 / g.a_band[ia]));
                     if (g.b_ready[ib] >= 0)
-                        wait_flag_ge<false>(g.ready + g.b_ready[ib] + n0 / g.b_band[ib], g.ready_val, g.timeout_ns, g.status);
+                        wait_flag_ge<false>(g.ready + g.b_ready[ib] + n0 / g.b_band[ib], g.ready_val, g.timeout_ns, g.status,
+                                            (1ull << 56) | (2ull << 48) | (unsigned long long)(g.b_ready[ib] + n0 / g.b_band[ib]));
                     const CUtensorMap* mA = &g.mapA[ia];
                     const CUtensorMap* mB = &g.mapB[ib];
                     const int nkb = en.nkb[sg];
@@ -462,7 +464,7 @@ gemm_f64_dmma_grouped_kernel(const __grid_constant__ G2Params g) {
         const int Mc = en.M, Nc = en.N;
         if (Ci != nullptr && en.cin_flag != nullptr && en.cin_flag != cin_seen) {
             // the other holder's partial must have landed in this GPU's staging buffer (every lane acquires)
-            wait_flag_ge<true>(en.cin_flag, en.cin_val, g.timeout_ns, g.status);
+            wait_flag_ge<true>(en.cin_flag, en.cin_val, g.timeout_ns, g.status, (1ull << 56) | (3ull << 48) | (unsigned long long)c);
             cin_seen = en.cin_flag;
         }
         const bool vec_ok = ((reinterpret_cast<uintptr_t>(Db) & 15) == 0) && ((ldd & 1) == 0) &&

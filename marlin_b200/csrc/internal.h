@@ -61,9 +61,12 @@ unsigned long long ipc_evictions();
 cudaError_t ipc_close(const unsigned char handle[64]);
 cudaError_t ipc_close_all();
 cudaError_t flag_signal(void* flag, unsigned long long v, cudaStream_t st);
+bool stream_memops_available();
+cudaError_t stream_write64(void* flag, unsigned long long v, cudaStream_t st);
+cudaError_t stream_wait64_geq(const void* flag, unsigned long long v, cudaStream_t st);
 cudaError_t flag_wait(const void* flag, unsigned long long v, cudaStream_t st);
 cudaError_t flag_wait_bounded(const void* flag, unsigned long long v, long long timeout_ns, unsigned long long* status,
-                              cudaStream_t st);
+                              cudaStream_t st, unsigned long long tag = 0);
 }  // namespace mb
 
 // thread-local message of the last failing call (defined in capi.cu)

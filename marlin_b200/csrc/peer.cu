@@ -24,7 +24,7 @@ __global__ void flag_signal_kernel(unsigned long long* flag, unsigned long long 
 // Bounded wait: after timeout_ns (0 = forever) the kernel sets *status = 2 and returns, so a rank whose peer died
 // mid-multiply gets an error code from the next mb_comm_check / multiply call instead of a GPU that cannot be interrupted.
 __global__ void flag_wait_kernel(const unsigned long long* flag, unsigned long long v, long long timeout_ns,
-                                 unsigned long long* status) {
+                                 unsigned long long* status, unsigned long long tag) {
     unsigned long long cur, t0 = 0;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
     for (unsigned spins = 0;; ++spins) {
@@ -35,7 +35,7 @@ __global__ void flag_wait_kernel(const unsigned long long* flag, unsigned long l
             unsigned long long now;
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
             if ((long long)(now - t0) > timeout_ns) {
-                if (status) *status = 2ull;
+                if (status) *status = tag ? tag : 2ull;      // which wait gave up (first one wins is not needed: any is a lead)
                 break;
             }
         }
@@ -146,17 +146,47 @@ cudaError_t ipc_close_all() {
     return cudaSuccess;
 }
 
+// ---- stream memory operations: flag writes and waits executed by the front end / copy engines, NOT by kernels ----
+// A tiny kernel launched on a side stream while a persistent kernel holds every SM may never be scheduled (measured:
+// scripts/probe_copy_under_persistent.cu — a 1-thread kernel submitted right after the resident grid stays blocked until
+// that grid retires, and blocks later launches behind it), so nothing the resident GEMM waits for may depend on one.
+typedef CUresult (*StreamWrite64Fn)(CUstream, CUdeviceptr, cuuint64_t, unsigned int);
+typedef CUresult (*StreamWait64Fn)(CUstream, CUdeviceptr, cuuint64_t, unsigned int);
+static StreamWrite64Fn g_write64 = nullptr;
+static StreamWait64Fn g_wait64 = nullptr;
+bool stream_memops_available() {
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuStreamWriteValue64", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            g_write64 = reinterpret_cast<StreamWrite64Fn>(p);
+        p = nullptr;
+        if (cudaGetDriverEntryPoint("cuStreamWaitValue64", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            g_wait64 = reinterpret_cast<StreamWait64Fn>(p);
+    });
+    return g_write64 != nullptr && g_wait64 != nullptr;
+}
+cudaError_t stream_write64(void* flag, unsigned long long v, cudaStream_t st) {
+    if (!stream_memops_available()) return cudaErrorNotSupported;
+    return g_write64(st, reinterpret_cast<CUdeviceptr>(flag), v, CU_STREAM_WRITE_VALUE_DEFAULT) == CUDA_SUCCESS ? cudaSuccess : cudaErrorNotSupported;
+}
+cudaError_t stream_wait64_geq(const void* flag, unsigned long long v, cudaStream_t st) {
+    if (!stream_memops_available()) return cudaErrorNotSupported;
+    return g_wait64(st, reinterpret_cast<CUdeviceptr>(flag), v, CU_STREAM_WAIT_VALUE_GEQ) == CUDA_SUCCESS ? cudaSuccess : cudaErrorNotSupported;
+}
+
 cudaError_t flag_signal(void* flag, unsigned long long v, cudaStream_t st) {
     flag_signal_kernel<<<1, 1, 0, st>>>(static_cast<unsigned long long*>(flag), v);
     return cudaGetLastError();
 }
 cudaError_t flag_wait(const void* flag, unsigned long long v, cudaStream_t st) {
-    flag_wait_kernel<<<1, 1, 0, st>>>(static_cast<const unsigned long long*>(flag), v, 0, nullptr);
+    flag_wait_kernel<<<1, 1, 0, st>>>(static_cast<const unsigned long long*>(flag), v, 0, nullptr, 0);
     return cudaGetLastError();
 }
 cudaError_t flag_wait_bounded(const void* flag, unsigned long long v, long long timeout_ns, unsigned long long* status,
-                              cudaStream_t st) {
-    flag_wait_kernel<<<1, 1, 0, st>>>(static_cast<const unsigned long long*>(flag), v, timeout_ns, status);
+                              cudaStream_t st, unsigned long long tag) {
+    flag_wait_kernel<<<1, 1, 0, st>>>(static_cast<const unsigned long long*>(flag), v, timeout_ns, status, tag);
     return cudaGetLastError();
 }
 

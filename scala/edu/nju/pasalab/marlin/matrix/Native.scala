@@ -61,6 +61,7 @@ object Native {
   @native def commDestroy(comm: Long): Unit
   @native def commBarrier(comm: Long): Unit
   @native def commCheck(comm: Long): Unit
+  @native def commAbort(comm: Long): Unit
   @native def distPlan(m: Int, k: Int, n: Int, world: Int): Array[Int] // m*k*n product ranks, then m*n C owners
   @native def matmulBlockedDist(comm: Long, aTiles: Array[Long], aOwner: Array[Int], bTiles: Array[Long],
                                 bOwner: Array[Int], m: Int, k: Int, n: Int, rowLen: Array[Int], kLen: Array[Int],

@@ -161,6 +161,59 @@ def main():
             nat.check(lib.mb_comm_barrier(comm))
         for t in mine:
             nat.check(lib.mb_host_free_shared(f"{session}_{ci}_{t}".encode(), shared[t][0], shared[t][1], 1 if co[t] == rank else 0))
+    # ---- optional: the bench-sized end-to-end case (MB_BIG=n): pinned shared host tiles on BOTH sides, so every copy is
+    #      truly asynchronous and the grouped GEMM is resident long before its operands arrive; checked with Freivalds ----
+    big = int(os.environ.get("MB_BIG", "0"))
+    if big:
+        g = 2
+        bs = big // g
+        a_home = (C.c_int32 * (g * g))()
+        b_home = (C.c_int32 * (g * g))()
+        nat.check(lib.mb_dist_host_homes(g, g, g, world, a_home, b_home))
+        pr = (C.c_int32 * (g * g * g))()
+        co = (C.c_int32 * (g * g))()
+        nat.check(lib.mb_dist_plan(g, g, g, world, pr, co))
+
+        def shared(tag, t):
+            ptr = C.c_void_p()
+            nat.check(lib.mb_host_alloc_shared(f"{session}_{tag}{t}".encode(), bs * bs * 8, C.byref(ptr)))
+            return ptr, np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_double)), shape=(bs, bs)).T      # column-major view
+
+        tiles = {}
+        for tag, homes in (("A", a_home), ("B", b_home)):
+            for t in range(g * g):
+                ptr, view = shared(tag, t)                       # every rank maps every input tile (rank 0 fills them all)
+                tiles[(tag, t)] = (ptr, view)
+        if rank == 0:
+            r2 = np.random.default_rng(99)
+            for (tag, t), (_, view) in tiles.items():
+                view[...] = r2.random((bs, bs))
+        ctiles = {t: shared("C", t) for t in range(g * g)}
+        nat.check(lib.mb_comm_barrier(comm))
+        pa = (C.c_void_p * (g * g))(*[tiles[("A", t)][0] if a_home[t] == rank else None for t in range(g * g)])
+        pb = (C.c_void_p * (g * g))(*[tiles[("B", t)][0] if b_home[t] == rank else None for t in range(g * g)])
+        mine = sorted({s_ // g for s_ in range(g * g * g) if pr[s_] == rank})
+        pc = (C.c_void_p * (g * g))(*[ctiles[t][0] if t in mine else None for t in range(g * g)])
+        lens = (C.c_int32 * g)(*([bs] * g))
+        import time
+        for rep in range(3):
+            nat.check(lib.mb_comm_barrier(comm))
+            t0 = time.perf_counter()
+            nat.check(lib.mb_matmul_blocked_dist_host(comm, pa, a_home, pb, b_home, g, g, g, lens, lens, lens, pc))
+            nat.check(lib.mb_comm_barrier(comm))
+            dt = time.perf_counter() - t0
+            if rank == 0:
+                print(f"big e2e {big}^2 on {world} ranks / {ndev} GPU(s): {dt * 1e3:.1f} ms = {2.0 * big ** 3 / dt / 1e12:.1f} TFLOP/s", flush=True)
+        if rank == 0:
+            Afull = np.block([[tiles[("A", i * g + kk)][1] for kk in range(g)] for i in range(g)])
+            Bfull = np.block([[tiles[("B", kk * g + j)][1] for j in range(g)] for kk in range(g)])
+            Cfull = np.block([[ctiles[i * g + j][1] for j in range(g)] for i in range(g)])
+            x = np.random.default_rng(3).random(big)
+            lhs, rhs = Cfull @ x, Afull @ (Bfull @ x)
+            err = (np.abs(lhs - rhs) / rhs).max()
+            assert err <= 1e-10, ("big", err)
+            print(f"big e2e parity (Freivalds) {err:.2e}", flush=True)
+        nat.check(lib.mb_comm_barrier(comm))
     nat.check(lib.mb_comm_barrier(comm))
     nat.check(lib.mb_comm_destroy(comm))
     nat.check(lib.mb_shutdown(ctx))

@@ -13,9 +13,10 @@ pytestmark = pytest.mark.gpu
 ROOT = Path(__file__).resolve().parents[1]
 
 
-def _run(world, ndev, slow, timeout=900):
+def _run(world, ndev, slow, timeout=900, big=0):
     session = uuid.uuid4().hex[:16]
-    env = dict(os.environ, MARLIN_B200_TIMEOUT_S="90", MARLIN_B200_DIST_SLOW="1" if slow else "0")
+    env = dict(os.environ, MARLIN_B200_TIMEOUT_S="90", MARLIN_B200_DIST_SLOW="1" if slow else "0", MB_BIG=str(big),
+               CUDA_DEVICE_MAX_CONNECTIONS="32")
     procs = [subprocess.Popen([sys.executable, str(ROOT / "tests" / "dist_cabi_worker.py"), str(r), str(world), session, str(ndev)],
                               stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env) for r in range(world)]
     outs = []
@@ -29,6 +30,7 @@ def _run(world, ndev, slow, timeout=900):
         outs.append((p.returncode, out))
     for r, (rc, out) in enumerate(outs):
         assert rc == 0 and f"cabi rank {r}/{world} ok" in out, f"rank {r}:\n{out[-3000:]}"
+    return outs
 
 
 @pytest.mark.parametrize("slow", [False, True])
@@ -46,3 +48,13 @@ def test_dist_multiply_cabi_all_gpus():
     if ndev < 3:
         pytest.skip("needs >= 3 GPUs (the 2-rank case runs everywhere)")
     _run(min(ndev, 8), min(ndev, 8), False)
+
+
+def test_dist_host_path_bench_size_pinned():
+    """The end-to-end entry at a bench-like size (8192^2, 2x2 grid: 4096^2 tiles, four bands each) with PINNED shared host
+    tiles: all copies are asynchronous, so each rank's grouped GEMM is resident and spinning on band flags long before the
+    first band lands — the situation in which a flag written by a kernel (instead of a stream memory operation) deadlocks."""
+    import torch
+    ndev = torch.cuda.device_count()
+    outs = _run(2, min(2, ndev), False, big=8192)
+    assert "big e2e parity" in outs[0][1]

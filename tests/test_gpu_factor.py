@@ -112,7 +112,7 @@ def test_inverse_matches_lapack(gpu, n):
     got = download(gpu, o, n, n)
     want = np.linalg.inv(A)
     assert np.abs(got - want).max() <= 1e-10 * np.abs(want).max()
-    assert np.abs(A @ got - np.eye(n)).max() <= 1e-11
+    assert np.abs(A @ got - np.eye(n)).max() <= 1e-10
 
 
 def test_inverse_suite_golden_and_singular(gpu):
