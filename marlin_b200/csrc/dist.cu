@@ -173,7 +173,7 @@ cudaError_t sig(mb_comm* c, unsigned long long* flag, unsigned long long v, cuda
     }
     unsigned long long* slot = c->ring + (c->ring_pos++ % RING_SLOTS);
     *slot = v;
-    return cudaMemcpyAsync(flag, slot, 8, cudaMemcpyHostToDevice, st);
+    return cudaMemcpyAsync(flag, slot, 8, cudaMemcpyDefault, st);
 }
 // Unbounded on the device (a memory operation cannot time out); a rank that loses its peers notices at the next host-side
 // rendezvous (bounded) and mb_comm_abort() releases whatever is still queued.

@@ -159,3 +159,39 @@ def test_dist_plan_matches_python_plan():
                     assert pr[i * n * k + j * k + kk] == r
             for (i, j), o in plan.c_owner.items():
                 assert co[i * n + j] == o
+
+
+def test_dist_host_homes_is_a_balanced_matching():
+    """mb_dist_host_homes: every input tile is uploaded by one of the ranks that multiply with it, and the uploads are
+    spread as evenly over the ranks (PCIe links) as those constraints allow — e.g. the headline (2,2,2) grid on 8 GPUs
+    gives every rank exactly one of the eight tiles."""
+    import ctypes as C
+    lib = nat.load()
+    for (m, k, n) in [(2, 2, 2), (1, 2, 1), (4, 4, 4), (3, 2, 2), (1, 8, 1), (2, 1, 3)]:
+        for world in (1, 2, 4, 8):
+            pr = (C.c_int32 * (m * k * n))()
+            assert lib.mb_dist_plan(m, k, n, world, pr, None) == 0
+            ah = (C.c_int32 * (m * k))()
+            bh = (C.c_int32 * (k * n))()
+            assert lib.mb_dist_host_homes(m, k, n, world, ah, bh) == 0
+            need_a = {t: set() for t in range(m * k)}
+            need_b = {t: set() for t in range(k * n)}
+            for i in range(m):
+                for j in range(n):
+                    for kk in range(k):
+                        r = pr[i * n * k + j * k + kk]
+                        need_a[i * k + kk].add(r)
+                        need_b[kk * n + j].add(r)
+            loads = [0] * world
+            for t in range(m * k):
+                assert ah[t] in need_a[t]
+                loads[ah[t]] += 1
+            for t in range(k * n):
+                assert bh[t] in need_b[t]
+                loads[bh[t]] += 1
+            active = {r for s_ in (need_a, need_b) for v in s_.values() for r in v}
+            assert max(loads) <= -(-(m * k + k * n) // len(active)) + 1, (m, k, n, world, loads)
+    ah = (C.c_int32 * 4)()
+    bh = (C.c_int32 * 4)()
+    assert lib.mb_dist_host_homes(2, 2, 2, 8, ah, bh) == 0
+    assert sorted(list(ah) + list(bh)) == list(range(8))         # one tile per GPU
