@@ -26,6 +26,7 @@
 #include <unistd.h>
 
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <map>
@@ -203,6 +204,31 @@ int32_t sync_bounded(mb_comm* c, cudaStream_t st, const char* what) {
         if (e != cudaErrorNotReady) return cuda_fail(e, what);
         if (spins > 200) usleep(50);
         if (now_s() - t0 > c->timeout_s) {
+            // post-mortem for the log: which flag words have reached the current epoch
+            {
+                cudaStream_t t = nullptr;
+                std::vector<unsigned long long> snap(FLAG_WORDS, 0);
+                if (cudaStreamCreateWithFlags(&t, cudaStreamNonBlocking) == cudaSuccess) {
+                    cudaMemcpyAsync(snap.data(), c->flags, sizeof(unsigned long long) * FLAG_WORDS, cudaMemcpyDeviceToHost, t);
+                    cudaStreamSynchronize(t);
+                    cudaStreamDestroy(t);
+                    auto dump = [&](const char* name, int base, int count) {
+                        fprintf(stderr, "[marlin_b200 rank %d epoch %llu] %s:", c->rank, c->epoch, name);
+                        for (int i = 0; i < count; ++i) if (snap[base + i]) fprintf(stderr, " [%d]=%llu", i, snap[base + i]);
+                        fprintf(stderr, "\n");
+                    };
+                    dump("channels", F_CH, 4 * MAXW);
+                    dump("upready", F_UPREADY, MAXW * UP_SLOTS * MAX_BANDS);
+                    dump("subdone", F_SUBDONE, MAXW * SUB_SLOTS);
+                    dump("band", F_BAND, 2 * mb::G2_MAX_OPS * MAX_BANDS);
+                    dump("ctr", F_CTR, mb::G2_MAX_ENTRIES);
+                    dump("sig", F_SIG, mb::G2_MAX_ENTRIES);
+                    dump("status", F_STATUS, 8);
+                    fprintf(stderr, "[marlin_b200 rank %d] stream states: S=%d X=%d R=%d U=%d (0 = idle, 600 = busy)\n", c->rank,
+                            (int)cudaStreamQuery(c->ctx->stream), (int)cudaStreamQuery(c->X), (int)cudaStreamQuery(c->R),
+                            c->ctx->h2d_stream ? (int)cudaStreamQuery(c->ctx->h2d_stream) : -1);
+                }
+            }
             abort_local(c);
             cudaStreamSynchronize(st);
             return fail(MB_ERR_TIMEOUT, "%s: no progress for %.0f s (a peer died or fell out of step); the communicator has been aborted", what,
