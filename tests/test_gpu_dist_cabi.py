@@ -56,5 +56,9 @@ def test_dist_host_path_bench_size_pinned():
     first band lands — the situation in which a flag written by a kernel (instead of a stream memory operation) deadlocks."""
     import torch
     ndev = torch.cuda.device_count()
-    outs = _run(2, min(2, ndev), False, big=8192)
+    if ndev < 2:
+        # two processes time-slicing ONE GPU make no useful progress here: each context's resident GEMM spins through its
+        # time slices while the other context's copies and memory operations wait for theirs
+        pytest.skip("needs 2 GPUs (the small host-path cases of the two-rank test run on one)")
+    outs = _run(2, 2, False, big=8192)
     assert "big e2e parity" in outs[0][1]
