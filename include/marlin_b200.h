@@ -76,6 +76,11 @@ int32_t mb_block_download(mb_ctx* ctx, const mb_block* blk, double* host, int32_
 int32_t mb_block_free(mb_ctx* ctx, mb_block* blk);
 int32_t mb_block_info(const mb_block* blk, int32_t* rows, int32_t* cols, int32_t* ld,
                       int32_t* is_transpose, int32_t* dtype, void** device_ptr);
+/* Optional: a cudaEvent_t that completes when the block's contents are final (blocks are immutable values, like the
+ * blocks of a cached RDD).  mb_matmul_blocked_dist then offers such tiles to the other ranks as soon as that event has
+ * completed instead of after everything queued on the ctx stream — the pulls of multiply s+1 overlap the products of
+ * multiply s.  The event must outlive the calls that use the block; NULL (default) = ordered on the ctx stream. */
+int32_t mb_block_set_ready_event(mb_block* blk, void* cuda_event);
 /* Breeze `.t` (no copy) and `m(r0 until r1, c0 until c1)` (a view, majorStride = parent rows),
  * as used by BlockMatrix.scala:198,213,299. */
 int32_t mb_block_view_t(mb_ctx* ctx, const mb_block* blk, mb_block** out);

@@ -49,6 +49,7 @@ SIGNATURES = {
     "mb_block_free": (c_i32, [c_ctx, c_blk]),
     "mb_block_info": (c_i32, [c_blk, C.POINTER(c_i32), C.POINTER(c_i32), C.POINTER(c_i32), C.POINTER(c_i32),
                               C.POINTER(c_i32), C.POINTER(C.c_void_p)]),
+    "mb_block_set_ready_event": (c_i32, [c_blk, C.c_void_p]),
     "mb_block_view_t": (c_i32, [c_ctx, c_blk, C.POINTER(c_blk)]),
     "mb_block_slice": (c_i32, [c_ctx, c_blk, c_i32, c_i32, c_i32, c_i32, C.POINTER(c_blk)]),
     "mb_block_gemm": (c_i32, [c_ctx, c_blk, c_blk, c_blk, c_i32]),

@@ -282,6 +282,12 @@ int32_t mb_block_info(const mb_block* blk, int32_t* rows, int32_t* cols, int32_t
     return MB_OK;
 }
 
+int32_t mb_block_set_ready_event(mb_block* blk, void* cuda_event) {
+    if (!blk) return fail(MB_ERR_INVALID_ARG, "null block");
+    blk->ready_event = cuda_event;
+    return MB_OK;
+}
+
 int32_t mb_block_view_t(mb_ctx* ctx, const mb_block* blk, mb_block** out) {
     if (!ctx || !blk || !out) return fail(MB_ERR_INVALID_ARG, "mb_block_view_t: null argument");
     int32_t r = new_block(out);

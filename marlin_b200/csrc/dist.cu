@@ -103,7 +103,7 @@ struct mb_comm {
     size_t shm_bytes = 0;
     unsigned long long* flags = nullptr;             // local flag words (device)
     unsigned long long* flags_peer[MAXW] = {};
-    cudaStream_t X = nullptr, R = nullptr;           // copy stream, reduce / download stream
+    cudaStream_t X = nullptr, R = nullptr, G = nullptr;   // copy stream, download stream, READY stream (tiles with ready events)
     char* staging = nullptr;                         // [src][slot_bytes]
     size_t slot_bytes = 0;
     char* staging_peer[MAXW] = {};
@@ -114,6 +114,8 @@ struct mb_comm {
     unsigned long long last_write_epoch[MAXW] = {};  // last epoch in which I stored into dst's staging
     cudaEvent_t ev_compute = nullptr, ev_tmp = nullptr;
     bool have_compute = false;
+    cudaEvent_t ev_half[2] = {nullptr, nullptr};     // device path: the products that read arena half p have been issued
+    bool have_half[2] = {false, false};
     unsigned long long* status_host = nullptr;       // pinned copy of flags[F_STATUS]
     double timeout_s = 120.0;
     std::vector<cudaEvent_t> events;                 // pool, reused every call
@@ -403,6 +405,9 @@ int32_t mb_comm_init(mb_ctx* ctx, int32_t rank, int32_t world, const char* sessi
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->X, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->R, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->G, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_half[0], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_half[1], cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_compute, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_tmp, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaMallocHost(&c->status_host, 8);
@@ -458,6 +463,8 @@ int32_t mb_comm_destroy(mb_comm* c) {
     if (c->ev_tmp) cudaEventDestroy(c->ev_tmp);
     if (c->X) cudaStreamDestroy(c->X);
     if (c->R) cudaStreamDestroy(c->R);
+    if (c->G) cudaStreamDestroy(c->G);
+    for (int p = 0; p < 2; ++p) if (c->ev_half[p]) cudaEventDestroy(c->ev_half[p]);
     if (c->shm) munmap(c->shm, c->shm_bytes);
     delete c;
     return MB_OK;
@@ -661,8 +668,30 @@ int32_t mb_matmul_blocked_dist(mb_comm* c, mb_block* const* A_tiles, const int32
                     if (b_owner[kk * n + j] == rank) consumer[r] = 1;
                 }
             }
-    for (int p = 0; p < world; ++p)
-        if (consumer[p]) MB_CUDA(sig(c, flag_ch(c, p, CH_READY, rank), e, S));
+    {
+        // Tiles that carry a ready event are offered as soon as those events have completed (stream G), not after everything
+        // queued on S — so the pulls of this multiply can run under the products of the previous one.
+        bool all_events = true;
+        std::vector<void*> evs;
+        for (int i = 0; i < m && all_events; ++i)
+            for (int j = 0; j < n && all_events; ++j)
+                for (int kk = 0; kk < k && all_events; ++kk) {
+                    if (plan.prod_rank[i * n * k + j * k + kk] == rank) continue;
+                    if (a_owner[i * k + kk] == rank) { void* ev = A_tiles[i * k + kk]->ready_event; if (ev) evs.push_back(ev); else all_events = false; }
+                    if (b_owner[kk * n + j] == rank) { void* ev = B_tiles[kk * n + j]->ready_event; if (ev) evs.push_back(ev); else all_events = false; }
+                }
+        // READY is always written from stream G, so the epochs reach a consumer in order whichever rule a call used
+        if (all_events && !evs.empty()) {
+            std::sort(evs.begin(), evs.end());
+            evs.erase(std::unique(evs.begin(), evs.end()), evs.end());
+            for (void* ev : evs) MB_CUDA(cudaStreamWaitEvent(c->G, static_cast<cudaEvent_t>(ev), 0));
+        } else {
+            MB_CUDA(cudaEventRecord(c->ev_tmp, S));
+            MB_CUDA(cudaStreamWaitEvent(c->G, c->ev_tmp, 0));
+        }
+        for (int p = 0; p < world; ++p)
+            if (consumer[p]) MB_CUDA(sig(c, flag_ch(c, p, CH_READY, rank), e, c->G));
+    }
 
     // ---- 2. pull the tiles I need, in first-use order, band by band, on the copy stream ----
     std::vector<Tile> tA(m * k), tB(k * n);
@@ -694,15 +723,20 @@ int32_t mb_matmul_blocked_dist(mb_comm* c, mb_block* const* A_tiles, const int32
     for (int t = 0; t < m * k; ++t) if (needA[t]) setup_tile(tA[t], entA[t], A_tiles[t], true, a_owner[t]);
     for (int t = 0; t < k * n; ++t) if (needB[t]) setup_tile(tB[t], entB[t], B_tiles[t], false, b_owner[t]);
     if (flag_slot > 2 * mb::G2_MAX_OPS) fast = false;       // cannot happen before the operand limit below trips; kept for safety
-    if ((rc = ensure_arena(c, arena_need)) != MB_OK) return rc;
+    // two halves, alternating by epoch: the pulls of this call may land while the previous call's products still read theirs
+    const int half = (int)(e & 1);
+    const size_t half_need = up256(arena_need);
+    if (2 * half_need > c->arena_bytes) { c->have_half[0] = c->have_half[1] = false; }       // regrown below (device sync inside)
+    if ((rc = ensure_arena(c, 2 * half_need)) != MB_OK) return rc;
+    char* const arena_base = c->arena + (size_t)half * (c->arena_bytes / 2 / 256 * 256);
     for (auto& pr : pulls) {
         Tile& t = pr.first == 0 ? tA[pr.second] : tB[pr.second];
-        t.blk.data = c->arena + t.blk.offset * (long long)elem_size(t.blk.dtype);
+        t.blk.data = arena_base + t.blk.offset * (long long)elem_size(t.blk.dtype);
         t.blk.offset = 0;
     }
     if (!pulls.empty()) {
-        // the arena may still be read by the previous call's products
-        if (c->have_compute) MB_CUDA(cudaStreamWaitEvent(X, c->ev_compute, 0));
+        // this half was last read by the products of two calls ago (or by a host-path call, which is synchronous)
+        if (c->have_half[half]) MB_CUDA(cudaStreamWaitEvent(X, c->ev_half[half], 0));
         std::vector<char> waited(world, 0);
         // tiles of one product are interleaved band by band (A0 B0 A1 B1 ...); products follow one another
         size_t p0 = 0;
@@ -898,6 +932,8 @@ int32_t mb_matmul_blocked_dist(mb_comm* c, mb_block* const* A_tiles, const int32
     }
     MB_CUDA(cudaEventRecord(c->ev_compute, S));
     c->have_compute = true;
+    MB_CUDA(cudaEventRecord(c->ev_half[half], S));
+    c->have_half[half] = true;
 
     // ---- 4. the reduceByKey across ranks ----
     for (int p = 0; p < world; ++p) {

@@ -51,6 +51,7 @@ struct mb_block {
     int dtype = MB_F64;
     int owns = 0;
     int device = 0;
+    void* ready_event = nullptr;   // optional cudaEvent_t: the block's contents are final once it has completed
 };
 
 namespace mb {

@@ -332,7 +332,7 @@ class BlockMatrix(DistributedMatrix):
                     c_arr[i * n + j] = partial[(i, j)].handle()
         with profiling.phase("gemm"):
             nat.check(rt.lib.mb_matmul_blocked_dist(mesh.comm, a_arr, a_own, b_arr, b_own, m, k, n, row_len, k_len, col_len, dt, c_arr))
-        result = [(BlockID(i, j), blk) for (i, j), blk in sorted(partial.items())]
+        result = [(BlockID(i, j), blk.mark_ready()) for (i, j), blk in sorted(partial.items())]
         owners = {(i, j): c_owner[i * n + j] for i in range(m) for j in range(n)}
         return BlockMatrix(result, M, N, m, n, placement=lambda r, c, o=owners: o[(r, c)])
 

@@ -117,7 +117,23 @@ class SubMatrix:
             nat.check(rt.lib.mb_block_wrap(rt.ctx, C.c_void_p(self.buf.data_ptr()), self.offset, self._rows, self._cols,
                                            self.ld, int(self.is_transpose), self.dtype, C.byref(h)))
             self._handle = h
+            ev = getattr(self, "_ready_event", None)
+            if ev is not None:
+                nat.check(rt.lib.mb_block_set_ready_event(h, C.c_void_p(ev.cuda_event)))
         return self._handle
+
+    def mark_ready(self) -> "SubMatrix":
+        """Record that everything queued so far on the current stream produces this block's FINAL contents (blocks are
+        immutable values, like the blocks of a cached RDD): the multi-GPU multiply then offers the block to other ranks as
+        soon as this event completes instead of after all later work on the stream (see mb_block_set_ready_event)."""
+        if self.buf.is_cuda:
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(self.buf.device))
+            self._ready_event = ev
+            if self._handle is not None:
+                rt = Runtime.get()
+                nat.check(rt.lib.mb_block_set_ready_event(self._handle, C.c_void_p(ev.cuda_event)))
+        return self
 
     def __del__(self):
         h = getattr(self, "_handle", None)

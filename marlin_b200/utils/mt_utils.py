@@ -151,7 +151,7 @@ class MTUtils:
             MTUtils._fill(blk, seeds[idx], 0, dist_, row_major=False)
             if dtype != nat.MB_F64:
                 blk = blk.copy(dtype)
-            blocks.append((BlockID(i, j), blk))
+            blocks.append((BlockID(i, j), blk.mark_ready()))
         return BlockMatrix(blocks, nRows, nColumns, by_row, by_col)
 
     @staticmethod
