@@ -20,6 +20,7 @@
 #include "gemm_f64.h"
 #include "ptx.cuh"
 #include <atomic>
+#include <cstdlib>
 
 namespace mb {
 
@@ -297,6 +298,7 @@ struct G2Params {
     unsigned long long* status;                           // set to 1 if a wait times out
     long long timeout_ns;
     int ne, num_tiles;
+    int fence_all;                                        // 1: every thread fences its stores before the tile is counted
 };
 
 __device__ __forceinline__ unsigned long long ld_acquire_gpu(const unsigned long long* p) {
@@ -502,7 +504,11 @@ gemm_f64_dmma_grouped_kernel(const __grid_constant__ G2Params g) {
         }
         if (en.done_ctr != nullptr) {
             // every consumer thread's stores of this tile, then ONE thread counts the tile and, if it was the entry's last,
-            // publishes the completion flags with system scope (peer GPUs and the copy streams poll them)
+            // publishes the completion flags with system scope (peer GPUs and the copy streams poll them).
+            // EVERY thread fences its own stores first: they may be posted writes to a peer GPU still in flight on NVLink,
+            // and the fence of the one counting thread was measured not to hold them back (a flag overtook data at 8 GPUs:
+            // profiles/r02_bench_n8_parity_failure.json).
+            if (g.fence_all) __threadfence_system();
             asm volatile("bar.sync 1, %0;" ::"n"(NUM_CONSUMER_WARPS * 32) : "memory");
             if (cw == 0 && lane == 0) {
                 __threadfence_system();
@@ -735,6 +741,8 @@ cudaError_t gemm_f64_grouped2(const G2Launch& L, int num_sms, cudaStream_t strea
     g.ready = L.ready; g.ready_val = L.ready_val; g.status = L.status; g.timeout_ns = L.timeout_ns;
     g.ne = L.ne;
     g.num_tiles = tiles;
+    static const int fence_all = [] { const char* e = getenv("MARLIN_B200_FENCE_ALL"); return (e && e[0] == '0') ? 0 : 1; }();
+    g.fence_all = fence_all;
     static std::atomic<bool> attr_done{false};
     if (!attr_done.load(std::memory_order_acquire)) {
         cudaError_t e = cudaFuncSetAttribute(gemm_f64_dmma_grouped_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);

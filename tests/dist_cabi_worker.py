@@ -161,6 +161,58 @@ def main():
             nat.check(lib.mb_comm_barrier(comm))
         for t in mine:
             nat.check(lib.mb_host_free_shared(f"{session}_{ci}_{t}".encode(), shared[t][0], shared[t][1], 1 if co[t] == rank else 0))
+    # ---- optional: the fused GEMM + reduce-scatter at full size, back to back (MB_BIG_FUSED=n): an n x n product with the
+    #      contraction split over the two ranks ((1,2,1) grid), six multiplies queued without a host sync in between (flags,
+    #      staging slots and the remotely written C tile are reused from call to call), then Freivalds on the last result ----
+    bigf = int(os.environ.get("MB_BIG_FUSED", "0"))
+    if bigf and world == 2:
+        nn, kh = bigf, bigf // 2
+        a_own, b_own = [0, 1], [0, 1]
+        a_h = (nat.c_blk * 2)()
+        b_h = (nat.c_blk * 2)()
+        c_h = (nat.c_blk * 1)()
+        h = nat.c_blk()
+        nat.check(lib.mb_block_alloc(ctx, nn, kh, nat.MB_F64, C.byref(h)))
+        nat.check(lib.mb_fill_uniform(ctx, h, 1000 + rank, 0, 0.0, 1.0, 0))
+        a_h[rank] = h
+        h2 = nat.c_blk()
+        nat.check(lib.mb_block_alloc(ctx, kh, nn, nat.MB_F64, C.byref(h2)))
+        nat.check(lib.mb_fill_uniform(ctx, h2, 2000 + rank, 0, 0.0, 1.0, 0))
+        b_h[rank] = h2
+        co = (C.c_int32 * 1)()
+        nat.check(lib.mb_dist_plan(1, 2, 1, world, None, co))
+        cs = []
+        for rep in range(6):
+            if co[0] == rank:
+                hc = nat.c_blk()
+                nat.check(lib.mb_block_alloc(ctx, nn, nn, nat.MB_F64, C.byref(hc)))
+                cs.append(hc)
+                c_h[0] = hc
+            nat.check(lib.mb_matmul_blocked_dist(comm, a_h, (C.c_int32 * 2)(*a_own), b_h, (C.c_int32 * 2)(*b_own), 1, 2, 1,
+                                                 (C.c_int32 * 1)(nn), (C.c_int32 * 2)(kh, kh), (C.c_int32 * 1)(nn), nat.MB_F64, c_h))
+        nat.check(lib.mb_synchronize(ctx))
+        nat.check(lib.mb_comm_check(comm))
+        # gather x-products on the host: y = C x on the owner, z = sum_kk A_kk (B_kk x) from both ranks through shared memory
+        x = np.random.default_rng(11).random(nn)
+        Ak = np.empty((nn, kh), order="F")
+        Bk = np.empty((kh, nn), order="F")
+        nat.check(lib.mb_block_download(ctx, a_h[rank], Ak.ctypes.data_as(C.c_void_p), nn))
+        nat.check(lib.mb_block_download(ctx, b_h[rank], Bk.ctypes.data_as(C.c_void_p), kh))
+        ptr = C.c_void_p()
+        nat.check(lib.mb_host_alloc_shared(f"{session}_z".encode(), 2 * nn * 8, C.byref(ptr)))
+        zsh = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_double)), shape=(2, nn))
+        zsh[rank, :] = Ak @ (Bk @ x)
+        nat.check(lib.mb_comm_barrier(comm))
+        if co[0] == rank:
+            z = zsh[0] + zsh[1]
+            for idx in (0, len(cs) - 1):
+                Cm = np.empty((nn, nn), order="F")
+                nat.check(lib.mb_block_download(ctx, cs[idx], Cm.ctypes.data_as(C.c_void_p), nn))
+                err = (np.abs(Cm @ x - z) / z).max()
+                print(f"big fused {nn}^2 call {idx}: Freivalds scaled error {err:.2e}", flush=True)
+                assert err <= 1e-10, ("big fused", idx, err)
+        nat.check(lib.mb_comm_barrier(comm))
+
     # ---- optional: the bench-sized end-to-end case (MB_BIG=n): pinned shared host tiles on BOTH sides, so every copy is
     #      truly asynchronous and the grouped GEMM is resident long before its operands arrive; checked with Freivalds ----
     big = int(os.environ.get("MB_BIG", "0"))

@@ -13,10 +13,10 @@ pytestmark = pytest.mark.gpu
 ROOT = Path(__file__).resolve().parents[1]
 
 
-def _run(world, ndev, slow, timeout=900, big=0):
+def _run(world, ndev, slow, timeout=900, big=0, big_fused=0, extra_env=None):
     session = uuid.uuid4().hex[:16]
     env = dict(os.environ, MARLIN_B200_TIMEOUT_S="90", MARLIN_B200_DIST_SLOW="1" if slow else "0", MB_BIG=str(big),
-               CUDA_DEVICE_MAX_CONNECTIONS="32")
+               CUDA_DEVICE_MAX_CONNECTIONS="32", MB_BIG_FUSED=str(big_fused), **(extra_env or {}))
     procs = [subprocess.Popen([sys.executable, str(ROOT / "tests" / "dist_cabi_worker.py"), str(r), str(world), session, str(ndev)],
                               stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env) for r in range(world)]
     outs = []
@@ -62,3 +62,14 @@ def test_dist_host_path_bench_size_pinned():
         pytest.skip("needs 2 GPUs (the small host-path cases of the two-rank test run on one)")
     outs = _run(2, 2, False, big=8192)
     assert "big e2e parity" in outs[0][1]
+
+
+def test_fused_reduce_scatter_full_size_back_to_back():
+    """8192^2 with the contraction split over two GPUs, six multiplies queued back to back: the GEMM epilogue stores the
+    peer's half over NVLink, the flag that announces it must not overtake those stores (every thread fences before its tile
+    is counted).  Freivalds on the first and the last result."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    outs = _run(2, 2, False, big_fused=8192)
+    assert "big fused" in "".join(o for _, o in outs)
