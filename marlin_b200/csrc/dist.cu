@@ -883,7 +883,8 @@ int32_t mb_matmul_blocked_dist(mb_comm* c, mb_block* const* A_tiles, const int32
                 fused_free_to[peer] = 1;
             }
         }
-        if (ok) {
+        static const bool split_phases = [] { const char* v = getenv("MARLIN_B200_FUSED_SPLIT"); return v && v[0] == '1'; }();
+        if (ok && !split_phases) {
             L.ready = c->flags + F_BAND; L.ready_val = e; L.status = c->flags + F_STATUS; L.timeout_ns = timeout_ns(c);
             MB_CUDA(cudaMemsetAsync(c->flags + F_CTR, 0, sizeof(unsigned long long) * mb::G2_MAX_ENTRIES, S));
             int launches = 0;
@@ -891,6 +892,42 @@ int32_t mb_matmul_blocked_dist(mb_comm* c, mb_block* const* A_tiles, const int32
             if (ce == cudaSuccess) { ctx->launches += launches; launched_fast = true; }
             else if (ce != cudaErrorNotSupported) return cuda_fail(ce, "gemm_f64_grouped2");
             else cudaGetLastError();
+        } else if (ok) {
+            // Two launches with the exchange flags BETWEEN them (MARLIN_B200_FUSED_SPLIT=1): the halves the peers reduce (and
+            // every plain region) first, then — once the peers' flags say their partials have landed — the halves reduced
+            // here.  Completion is a kernel boundary, the flags are stream memory operations: no in-kernel signalling.
+            static thread_local mb::G2Launch L0, L2;
+            L0 = L; L2 = L;
+            L0.ne = L2.ne = 0;
+            struct Note { int peer, slot; bool remote_final; };
+            std::vector<Note> wrote, need, final_to;
+            for (int x = 0; x < L.ne; ++x) {
+                mb::G2Entry en = L.E[x];
+                const Reg& rg = regs[x];
+                const auto& h = plan.holders[rg.id];
+                const int peer = h.size() == 2 ? (h[0] == rank ? h[1] : h[0]) : -1;
+                en.done_ctr = nullptr; en.sig_remote = nullptr; en.sig_local = nullptr; en.cin_flag = nullptr;
+                if (rg.phase == 2) {
+                    L2.E[L2.ne++] = en;
+                    need.push_back({peer, pair_slot[rg.id], false});
+                    if (h[0] != rank) final_to.push_back({peer, pair_slot[rg.id], true});
+                } else {
+                    L0.E[L0.ne++] = en;
+                    if (rg.phase == 0) wrote.push_back({peer, pair_slot[rg.id], false});
+                }
+            }
+            L0.ready = L2.ready = c->flags + F_BAND; L0.ready_val = L2.ready_val = e;
+            L0.status = L2.status = c->flags + F_STATUS; L0.timeout_ns = L2.timeout_ns = timeout_ns(c);
+            int launches = 0;
+            cudaError_t ce = L0.ne ? mb::gemm_f64_grouped2(L0, ctx->num_sms, S, &launches) : cudaSuccess;
+            if (ce != cudaSuccess) return cuda_fail(ce, "gemm_f64_grouped2 (first half)");
+            for (const Note& w : wrote) MB_CUDA(sig(c, c->flags_peer[w.peer] + F_PART2 + rank * MAX_PAIR + w.slot, e, S));
+            for (const Note& w : need) MB_CUDA(waitf(c, c->flags + F_PART2 + w.peer * MAX_PAIR + w.slot, e, S));
+            ce = L2.ne ? mb::gemm_f64_grouped2(L2, ctx->num_sms, S, &launches) : cudaSuccess;
+            if (ce != cudaSuccess) return cuda_fail(ce, "gemm_f64_grouped2 (second half)");
+            for (const Note& w : final_to) MB_CUDA(sig(c, c->flags_peer[w.peer] + F_FINAL2 + rank * MAX_PAIR + w.slot, e, S));
+            ctx->launches += launches;
+            launched_fast = true;
         }
         if (!launched_fast) {
             // every rank evaluates the same predicates, except TMA encode failures: make a divergence loud, not silent

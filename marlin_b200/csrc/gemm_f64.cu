@@ -298,6 +298,7 @@ struct G2Params {
     unsigned long long* status;                           // set to 1 if a wait times out
     long long timeout_ns;
     int ne, num_tiles;
+    int poll_mode;                                        // 0: every thread polls the addend flag, 1: lane 0 + __syncwarp
     int fence_all;                                        // 1: every thread fences its stores before the tile is counted
 };
 
@@ -466,7 +467,9 @@ gemm_f64_dmma_grouped_kernel(const __grid_constant__ G2Params g) {
         const int Mc = en.M, Nc = en.N;
         if (Ci != nullptr && en.cin_flag != nullptr && en.cin_flag != cin_seen) {
             // the other holder's partial must have landed in this GPU's staging buffer (every lane acquires)
-            wait_flag_ge<true>(en.cin_flag, en.cin_val, g.timeout_ns, g.status, (1ull << 56) | (3ull << 48) | (unsigned long long)c);
+            if (g.poll_mode == 0 || lane == 0)
+                wait_flag_ge<true>(en.cin_flag, en.cin_val, g.timeout_ns, g.status, (1ull << 56) | (3ull << 48) | (unsigned long long)c);
+            if (g.poll_mode != 0) __syncwarp();
             cin_seen = en.cin_flag;
         }
         const bool vec_ok = ((reinterpret_cast<uintptr_t>(Db) & 15) == 0) && ((ldd & 1) == 0) &&
@@ -743,6 +746,8 @@ cudaError_t gemm_f64_grouped2(const G2Launch& L, int num_sms, cudaStream_t strea
     g.num_tiles = tiles;
     static const int fence_all = [] { const char* e = getenv("MARLIN_B200_FENCE_ALL"); return (e && e[0] == '0') ? 0 : 1; }();
     g.fence_all = fence_all;
+    static const int poll_mode = [] { const char* e = getenv("MARLIN_B200_CIN_POLL"); return (e && e[0] == '1') ? 1 : 0; }();
+    g.poll_mode = poll_mode;
     static std::atomic<bool> attr_done{false};
     if (!attr_done.load(std::memory_order_acquire)) {
         cudaError_t e = cudaFuncSetAttribute(gemm_f64_dmma_grouped_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
