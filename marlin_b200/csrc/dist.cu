@@ -883,7 +883,11 @@ int32_t mb_matmul_blocked_dist(mb_comm* c, mb_block* const* A_tiles, const int32
                 fused_free_to[peer] = 1;
             }
         }
-        static const bool split_phases = [] { const char* v = getenv("MARLIN_B200_FUSED_SPLIT"); return v && v[0] == '1'; }();
+        // 0: one launch, in-kernel signalling and in-kernel addend wait; 1: two launches, flags are stream memory operations;
+        // 2: two launches, first half signals in-kernel, second half launched behind a stream wait; 3: two launches, stream
+        // signal after the first half, second half waits in-kernel (2 and 3 exist to locate the fault of 0)
+        static const int fused_variant = [] { const char* v = getenv("MARLIN_B200_FUSED_SPLIT"); return v ? atoi(v) : 0; }();
+        const bool split_phases = fused_variant != 0;
         if (ok && !split_phases) {
             L.ready = c->flags + F_BAND; L.ready_val = e; L.status = c->flags + F_STATUS; L.timeout_ns = timeout_ns(c);
             MB_CUDA(cudaMemsetAsync(c->flags + F_CTR, 0, sizeof(unsigned long long) * mb::G2_MAX_ENTRIES, S));
@@ -906,7 +910,9 @@ int32_t mb_matmul_blocked_dist(mb_comm* c, mb_block* const* A_tiles, const int32
                 const Reg& rg = regs[x];
                 const auto& h = plan.holders[rg.id];
                 const int peer = h.size() == 2 ? (h[0] == rank ? h[1] : h[0]) : -1;
-                en.done_ctr = nullptr; en.sig_remote = nullptr; en.sig_local = nullptr; en.cin_flag = nullptr;
+                if (fused_variant != 2 || rg.phase != 0) { en.done_ctr = nullptr; en.sig_remote = nullptr; en.sig_local = nullptr; }
+                if (fused_variant != 3) en.cin_flag = nullptr;
+                if (fused_variant == 3 && rg.phase == 2) { en.done_ctr = nullptr; en.sig_remote = nullptr; }
                 if (rg.phase == 2) {
                     L2.E[L2.ne++] = en;
                     need.push_back({peer, pair_slot[rg.id], false});
@@ -919,10 +925,11 @@ int32_t mb_matmul_blocked_dist(mb_comm* c, mb_block* const* A_tiles, const int32
             L0.ready = L2.ready = c->flags + F_BAND; L0.ready_val = L2.ready_val = e;
             L0.status = L2.status = c->flags + F_STATUS; L0.timeout_ns = L2.timeout_ns = timeout_ns(c);
             int launches = 0;
+            if (fused_variant == 2) MB_CUDA(cudaMemsetAsync(c->flags + F_CTR, 0, sizeof(unsigned long long) * mb::G2_MAX_ENTRIES, S));
             cudaError_t ce = L0.ne ? mb::gemm_f64_grouped2(L0, ctx->num_sms, S, &launches) : cudaSuccess;
             if (ce != cudaSuccess) return cuda_fail(ce, "gemm_f64_grouped2 (first half)");
-            for (const Note& w : wrote) MB_CUDA(sig(c, c->flags_peer[w.peer] + F_PART2 + rank * MAX_PAIR + w.slot, e, S));
-            for (const Note& w : need) MB_CUDA(waitf(c, c->flags + F_PART2 + w.peer * MAX_PAIR + w.slot, e, S));
+            if (fused_variant != 2) for (const Note& w : wrote) MB_CUDA(sig(c, c->flags_peer[w.peer] + F_PART2 + rank * MAX_PAIR + w.slot, e, S));
+            if (fused_variant != 3) for (const Note& w : need) MB_CUDA(waitf(c, c->flags + F_PART2 + w.peer * MAX_PAIR + w.slot, e, S));
             ce = L2.ne ? mb::gemm_f64_grouped2(L2, ctx->num_sms, S, &launches) : cudaSuccess;
             if (ce != cudaSuccess) return cuda_fail(ce, "gemm_f64_grouped2 (second half)");
             for (const Note& w : final_to) MB_CUDA(sig(c, c->flags_peer[w.peer] + F_FINAL2 + rank * MAX_PAIR + w.slot, e, S));
