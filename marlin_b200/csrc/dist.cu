@@ -886,7 +886,11 @@ int32_t mb_matmul_blocked_dist(mb_comm* c, mb_block* const* A_tiles, const int32
         // 0: one launch, in-kernel signalling and in-kernel addend wait; 1: two launches, flags are stream memory operations;
         // 2: two launches, first half signals in-kernel, second half launched behind a stream wait; 3: two launches, stream
         // signal after the first half, second half waits in-kernel (2 and 3 exist to locate the fault of 0)
-        static const int fused_variant = [] { const char* v = getenv("MARLIN_B200_FUSED_SPLIT"); return v ? atoi(v) : 0; }();
+        // Default 1.  Variant 0 (and 2) — completion counted INSIDE a kernel whose epilogue stores to peer memory — is
+        // faulty on this hardware/software stack: at 8192^2, roughly one call in three comes back with one 16 x 32 patch (the
+        // counting warp's first fragment pair, one k index of one tile) off by a single product term; 1 and 3 were exact in
+        // every run (profiles/r02_fused_variants_2gpu.md).  The cause is not understood; the variants stay for diagnosis.
+        static const int fused_variant = [] { const char* v = getenv("MARLIN_B200_FUSED_SPLIT"); return v ? atoi(v) : 1; }();
         const bool split_phases = fused_variant != 0;
         if (ok && !split_phases) {
             L.ready = c->flags + F_BAND; L.ready_val = e; L.status = c->flags + F_STATUS; L.timeout_ns = timeout_ns(c);
@@ -1332,8 +1336,10 @@ int32_t mb_matmul_blocked_dist_host(mb_comm* c, const double* const* A_host, con
         const auto& h = plan.holders[mc.id];
         if (h.size() == 2) { const int peer = h[0] == rank ? h[1] : h[0]; writes_to[peer] = 1; reads_from[peer] = 1; }
     }
+    // my partials of the sub-blocks the peer reduces are pushed into ITS staging buffer by my copy engine (stream R, below):
+    // it must have consumed what I pushed there last time
     for (int p = 0; p < world; ++p)
-        if (writes_to[p] && c->last_write_epoch[p]) MB_CUDA(waitf(c, flag_ch(c, rank, CH_FREE, p), c->last_write_epoch[p], S));
+        if (writes_to[p] && c->last_write_epoch[p]) MB_CUDA(waitf(c, flag_ch(c, rank, CH_FREE, p), c->last_write_epoch[p], R));
     static thread_local mb::G2Launch L;
     L = mb::G2Launch();
     auto op_of = [&](HTile& t, bool is_a) {
@@ -1396,10 +1402,11 @@ int32_t mb_matmul_blocked_dist_host(mb_comm* c, const double* const* A_host, con
                 en.cin_val = e;
             }
         } else {
-            const int peer = h[0] == rank ? h[1] : h[0];
-            en.D = reinterpret_cast<double*>(c->staging_peer[peer] + (size_t)rank * c->slot_bytes + slot_off[sb.id]) + (size_t)sb.n_off * ldc + sb.m_off;
-            en.ldd = ldc;
-            en.sig_remote = c->flags_peer[peer] + F_SUBDONE + rank * SUB_SLOTS + sb.sub_idx;
+            // a sub-block the PEER reduces: my partial goes to the same place in my own C buffer (local stores: completion
+            // counting next to peer stores proved unreliable, see mb_matmul_blocked_dist) and is pushed from there by the
+            // copy engine once the entry's completion flag is up
+            en.D = reinterpret_cast<double*>(c->arena + coff[sb.id]) + (size_t)sb.n_off * ldc + sb.m_off; en.ldd = ldc;
+            en.sig_local = c->flags + F_SIG + sb.entry;
         }
     }
     L.ready = c->flags + F_BAND; L.ready_val = e; L.status = c->flags + F_STATUS; L.timeout_ns = timeout_ns(c);
@@ -1414,15 +1421,23 @@ int32_t mb_matmul_blocked_dist_host(mb_comm* c, const double* const* A_host, con
     c->have_compute = true;
     for (int p = 0; p < world; ++p) if (writes_to[p]) c->last_write_epoch[p] = e;
 
-    // ---- download stream: finished (already reduced) sub-blocks -> host, hidden behind the rest of the GEMM ----
+    // ---- copy-out stream, in entry order: a finished sub-block is either mine (already reduced in the epilogue) -> host,
+    //      or the peer's -> pushed into its staging buffer over NVLink + its flag; all hidden behind the rest of the GEMM ----
     for (const Sub& sb : subs) {
-        if (!sb.mine) continue;
         const int i = sb.id / n;
         const int ldc = even(row_len[i]);
         MB_CUDA(waitf(c, c->flags + F_SIG + sb.entry, e, R));
-        const double* mine_ptr = reinterpret_cast<const double*>(c->arena + coff[sb.id]) + (size_t)sb.n_off * ldc + sb.m_off;
-        MB_CUDA(cudaMemcpy2DAsync(C_host[sb.id] + (size_t)sb.n_off * row_len[i] + sb.m_off, (size_t)row_len[i] * 8, mine_ptr, (size_t)ldc * 8,
-                                  (size_t)sb.M * 8, sb.N, cudaMemcpyDeviceToHost, R));
+        const double* src = reinterpret_cast<const double*>(c->arena + coff[sb.id]) + (size_t)sb.n_off * ldc + sb.m_off;
+        if (sb.mine) {
+            MB_CUDA(cudaMemcpy2DAsync(C_host[sb.id] + (size_t)sb.n_off * row_len[i] + sb.m_off, (size_t)row_len[i] * 8, src, (size_t)ldc * 8,
+                                      (size_t)sb.M * 8, sb.N, cudaMemcpyDeviceToHost, R));
+        } else {
+            const auto& h = plan.holders[sb.id];
+            const int peer = h[0] == rank ? h[1] : h[0];
+            double* dst = reinterpret_cast<double*>(c->staging_peer[peer] + (size_t)rank * c->slot_bytes + slot_off[sb.id]) + (size_t)sb.n_off * ldc + sb.m_off;
+            MB_CUDA(cudaMemcpy2DAsync(dst, (size_t)ldc * 8, src, (size_t)ldc * 8, (size_t)sb.M * 8, sb.N, cudaMemcpyDeviceToDevice, R));
+            MB_CUDA(sig(c, c->flags_peer[peer] + F_SUBDONE + rank * SUB_SLOTS + sb.sub_idx, e, R));
+        }
     }
     // the peer's staged partials have been consumed once my GEMM is done
     for (int p = 0; p < world; ++p)

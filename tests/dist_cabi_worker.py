@@ -241,55 +241,58 @@ def main():
     # ---- optional: the bench-sized end-to-end case (MB_BIG=n): pinned shared host tiles on BOTH sides, so every copy is
     #      truly asynchronous and the grouped GEMM is resident long before its operands arrive; checked with Freivalds ----
     big = int(os.environ.get("MB_BIG", "0"))
-    if big:
-        g = 2
-        bs = big // g
-        a_home = (C.c_int32 * (g * g))()
-        b_home = (C.c_int32 * (g * g))()
-        nat.check(lib.mb_dist_host_homes(g, g, g, world, a_home, b_home))
-        pr = (C.c_int32 * (g * g * g))()
-        co = (C.c_int32 * (g * g))()
-        nat.check(lib.mb_dist_plan(g, g, g, world, pr, co))
+    for grid in ([tuple(int(v) for v in g_.split(",")) for g_ in os.environ.get("MB_BIG_GRIDS", "2,2,2;1,2,1").split(";")] if big else []):
+        gm, gk, gn = grid
+        rl, kl, cl = big // gm, big // gk, big // gn
+        a_home = (C.c_int32 * (gm * gk))()
+        b_home = (C.c_int32 * (gk * gn))()
+        nat.check(lib.mb_dist_host_homes(gm, gk, gn, world, a_home, b_home))
+        pr = (C.c_int32 * (gm * gk * gn))()
+        co = (C.c_int32 * (gm * gn))()
+        nat.check(lib.mb_dist_plan(gm, gk, gn, world, pr, co))
+        tagg = f"{gm}{gk}{gn}"
 
-        def shared(tag, t):
+        def shared(tag, t, rows, cols):
             ptr = C.c_void_p()
-            nat.check(lib.mb_host_alloc_shared(f"{session}_{tag}{t}".encode(), bs * bs * 8, C.byref(ptr)))
-            return ptr, np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_double)), shape=(bs, bs)).T      # column-major view
+            nat.check(lib.mb_host_alloc_shared(f"{session}_{tagg}{tag}{t}".encode(), rows * cols * 8, C.byref(ptr)))
+            return ptr, np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_double)), shape=(cols, rows)).T      # column-major view
 
         tiles = {}
-        for tag, homes in (("A", a_home), ("B", b_home)):
-            for t in range(g * g):
-                ptr, view = shared(tag, t)                       # every rank maps every input tile (rank 0 fills them all)
-                tiles[(tag, t)] = (ptr, view)
+        for t in range(gm * gk):
+            tiles[("A", t)] = shared("A", t, rl, kl)            # every rank maps every input tile (rank 0 fills them all)
+        for t in range(gk * gn):
+            tiles[("B", t)] = shared("B", t, kl, cl)
         if rank == 0:
             r2 = np.random.default_rng(99)
             for (tag, t), (_, view) in tiles.items():
-                view[...] = r2.random((bs, bs))
-        ctiles = {t: shared("C", t) for t in range(g * g)}
+                view[...] = r2.random(view.shape)
+        ctiles = {t: shared("C", t, rl, cl) for t in range(gm * gn)}
         nat.check(lib.mb_comm_barrier(comm))
-        pa = (C.c_void_p * (g * g))(*[tiles[("A", t)][0] if a_home[t] == rank else None for t in range(g * g)])
-        pb = (C.c_void_p * (g * g))(*[tiles[("B", t)][0] if b_home[t] == rank else None for t in range(g * g)])
-        mine = sorted({s_ // g for s_ in range(g * g * g) if pr[s_] == rank})
-        pc = (C.c_void_p * (g * g))(*[ctiles[t][0] if t in mine else None for t in range(g * g)])
-        lens = (C.c_int32 * g)(*([bs] * g))
+        pa = (C.c_void_p * (gm * gk))(*[tiles[("A", t)][0] if a_home[t] == rank else None for t in range(gm * gk)])
+        pb = (C.c_void_p * (gk * gn))(*[tiles[("B", t)][0] if b_home[t] == rank else None for t in range(gk * gn)])
+        mine = sorted({s_ // gk for s_ in range(gm * gk * gn) if pr[s_] == rank})
+        pc = (C.c_void_p * (gm * gn))(*[ctiles[t][0] if t in mine else None for t in range(gm * gn)])
         import time
-        for rep in range(3):
+        for rep in range(4):
+            if rank == 0:
+                for t in range(gm * gn):
+                    ctiles[t][1][...] = np.nan
             nat.check(lib.mb_comm_barrier(comm))
             t0 = time.perf_counter()
-            nat.check(lib.mb_matmul_blocked_dist_host(comm, pa, a_home, pb, b_home, g, g, g, lens, lens, lens, pc))
+            nat.check(lib.mb_matmul_blocked_dist_host(comm, pa, a_home, pb, b_home, gm, gk, gn, (C.c_int32 * gm)(*([rl] * gm)),
+                                                      (C.c_int32 * gk)(*([kl] * gk)), (C.c_int32 * gn)(*([cl] * gn)), pc))
             nat.check(lib.mb_comm_barrier(comm))
             dt = time.perf_counter() - t0
             if rank == 0:
-                print(f"big e2e {big}^2 on {world} ranks / {ndev} GPU(s): {dt * 1e3:.1f} ms = {2.0 * big ** 3 / dt / 1e12:.1f} TFLOP/s", flush=True)
-        if rank == 0:
-            Afull = np.block([[tiles[("A", i * g + kk)][1] for kk in range(g)] for i in range(g)])
-            Bfull = np.block([[tiles[("B", kk * g + j)][1] for j in range(g)] for kk in range(g)])
-            Cfull = np.block([[ctiles[i * g + j][1] for j in range(g)] for i in range(g)])
-            x = np.random.default_rng(3).random(big)
-            lhs, rhs = Cfull @ x, Afull @ (Bfull @ x)
-            err = (np.abs(lhs - rhs) / rhs).max()
-            assert err <= 1e-10, ("big", err)
-            print(f"big e2e parity (Freivalds) {err:.2e}", flush=True)
+                print(f"big e2e {big}^2 grid {grid} on {world} ranks / {ndev} GPU(s): {dt * 1e3:.1f} ms = {2.0 * big ** 3 / dt / 1e12:.1f} TFLOP/s", flush=True)
+                Afull = np.block([[tiles[("A", i * gk + kk)][1] for kk in range(gk)] for i in range(gm)])
+                Bfull = np.block([[tiles[("B", kk * gn + j)][1] for j in range(gn)] for kk in range(gk)])
+                Cfull = np.block([[ctiles[i * gn + j][1] for j in range(gn)] for i in range(gm)])
+                x = np.random.default_rng(3 + rep).random(big)
+                lhs, rhs = Cfull @ x, Afull @ (Bfull @ x)
+                err = (np.abs(lhs - rhs) / rhs).max()
+                assert err <= 1e-10, ("big", grid, rep, err)
+                print(f"big e2e parity grid {grid} rep {rep} (Freivalds) {err:.2e}", flush=True)
         nat.check(lib.mb_comm_barrier(comm))
     nat.check(lib.mb_comm_barrier(comm))
     nat.check(lib.mb_comm_destroy(comm))
