@@ -6,7 +6,8 @@ Workload (BASELINE.json configs[2], the configuration the targets are quoted on,
 8192^3 (`BlockMatrix.multiply(other: BlockMatrix)`, matrix/BlockMatrix.scala:149-186), synthetic
 U[0,1) inputs from the on-device XORShift generator (MTUtils.randomBlockMatrix).  One step = one full
 multiply.  The same problem runs at N = 1, 2, 4, 8 GPUs ("strong" scaling); blocks are placed by
-MatrixElemOpPartitioner order mod N and tiles move with grouped NCCL send/recv.
+MatrixElemOpPartitioner order mod N; tiles move over NVLink peer memory behind the C ABI (mb_matmul_blocked_dist,
+csrc/dist.cu), with grouped NCCL send/recv only as the fallback transport (MARLIN_B200_TRANSPORT=nccl).
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--size S]          (N>1: launched by torchrun)
   python bench.py --impl reference ...   CPU restatement of the reference path (oracle port) on host cores
@@ -166,7 +167,8 @@ def workload_config(args, ws: int) -> dict:
            2: "2 GPUs: 4 products each, k-sum local; tiles pulled over NVLink peer memory",
            4: "4 GPUs: 2 products each (same C tile), k-sum local; tiles pulled over NVLink peer memory",
            8: "8 GPUs: 1 product each (RDD partition == GPU); A/B tiles pulled over NVLink peer memory (copy engines), the k=2 "
-              "partials reduce-scattered between the two holders by the GEMM epilogue's peer stores"}
+              "partials reduce-scattered between the two holders by the GEMM epilogues (two launches per step: the peer's halves "
+              "are stored into its HBM first, the own halves add the received partial in the epilogue)"}
     workload = (f"{N}x{N} fp64 BlockMatrix multiply, {g}x{g} block grid, (m,k,n)=({g},{g},{g}) "
                 f"[BASELINE.json configs[2]; also the 1-GPU target size]")
     if tall:
@@ -512,18 +514,26 @@ def run_ours(args):
         plan = comm.plan_multiply(g, g, g, ws, A.owner, B.owner)
         local_products = len(plan.products.get(rank, []))
         gemm_ms, gemm_n = phases.get("gemm", (0.0, 0))
-        launches_per_step = max(1, gemm_n // max(1, args.steps))
+        # kernels inside one timed "gemm" span: 1 at N = 1 (grouped launch); 2 where the k partials are reduce-scattered
+        # between two holders (the peer's halves first, flags as stream memory operations between the launches)
+        launches_per_step = max(1, gemm_n // max(1, args.steps), int(launches) // max(1, args.steps))
         flops_per_launch = local_products * 2.0 * bs ** 3 / launches_per_step
     gemm_avg_ms = gemm_ms / max(1, gemm_n)
+    spans_per_step = max(1, gemm_n // max(1, args.steps)) if not tall else 1
+    gemm_avg_ms = gemm_avg_ms * spans_per_step / launches_per_step           # per kernel launch
     achieved = flops_per_launch / (gemm_avg_ms * 1e-3) / 1e12 if gemm_n else None
     # DRAM traffic of that launch: ncu (--set full) measured dram read+write of ONE 8192^3 block product
-    # (profiles/r01_ncu_gemm_f64_dmma.md); a launch that covers several products is scaled by their count.
+    # (profiles/r01_ncu_gemm_f64_dmma.md, round-1 capture of the same kernel body; no round-2 capture exists);
+    # a launch that covers several products is scaled by their count.
     traffic = None
+    traffic_source = None
     summary = ROOT / "profiles" / "ncu_summary.json"
     if summary.exists() and not tall and (N, g) == (16384, 2):
         try:
             per_product = json.loads(summary.read_text()).get("gemm_f64_dmma", {}).get("dram_bytes_per_launch")
             traffic = per_product * local_products / launches_per_step if per_product else None
+            traffic_source = ("scaled from the round-1 ncu --set full capture of one 8192^3 block product "
+                              "(profiles/r01_ncu_gemm_f64_dmma.md); not re-captured for the grouped launch")
         except Exception:
             traffic = None
     peak, peak_src = FP64_PEAK_TFLOPS_MEASURED, None
@@ -535,11 +545,14 @@ def run_ours(args):
             peak, peak_src = 1400.0, "fallback sustained bf16 figure of B200_PROFILING.md"
         traffic = None
     roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                "frac": (achieved / peak) if achieved else None, "traffic": traffic,
+                "frac": (achieved / peak) if achieved else None, "traffic": traffic, "traffic_source": traffic_source,
                 "kernel": ("gemm_bf16_tcgen05_kernel<N,N> (tcgen05.mma kind::f16 + TMEM + TMA)" if bf16 else
                            ("gemm_f64_dmma_kernel<T,N> (row-major C = A*B as C^T = B^T*A^T)" if tall else
-                            "gemm_f64_dmma_grouped_kernel (DMMA.8x8x4 + TMA; one launch per rank and step" +
-                            ("" if ws == 1 else "; at N > 1 the timed span also holds the flag kernels of the exchange protocol and any wait for tiles / the peer's partial") + ")")),
+                            "gemm_f64_dmma_grouped_kernel (DMMA.8x8x4 + TMA; " +
+                            ("one launch per step" if ws == 1 else
+                             f"{launches_per_step} launch(es) per rank and step; launch_ms_avg = the CUDA-event span around them / their "
+                             "count, so it also holds the stream memory operations of the exchange protocol and any wait for "
+                             "tiles / the peer's partial") + ")")),
                 "launch_ms_avg": gemm_avg_ms,
                 "flops_per_launch": flops_per_launch, "launches_per_step": launches_per_step,
                 "peak_source": peak_src or "measured fp64 DMMA issue peak on this pool's B200 (scripts/dmma_bench.cu, "
@@ -645,8 +658,9 @@ def run_ours(args):
                     holders.setdefault(s_ // gk, set()).add(prank[s_])
                 d2h_box[0] = sum(bs_ * bs_ * 8 // len(holders[t]) for t in my_c)
                 path = ("mb_matmul_blocked_dist_host (C ABI): pinned host tiles -> banded H2D on the rank that homes a tile + NVLink pulls by "
-                        "the others -> one grouped DMMA launch per rank (starts on the first bands) -> per-sub-block reduce + D2H into shared "
-                        "pinned C tiles, every step")
+                        "the others -> one grouped DMMA launch per rank (starts on the first bands, sub-blocks in wavefront order) -> "
+                        "sub-blocks a peer reduces are pushed to it by copy engine and added in its epilogue (checkerboard) -> D2H "
+                        "into shared pinned C tiles, every step")
 
                 def e2e_step():
                     nat.check(lib.mb_matmul_blocked_dist_host(mesh.comm, pa, a_home, pb, b_home, g, gk, g, lens, lens, lens, pc))

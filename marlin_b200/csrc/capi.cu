@@ -1204,9 +1204,10 @@ int32_t mb_fill_uniform(mb_ctx* ctx, mb_block* blk, int64_t partition_seed, int6
     if (blk->dtype != MB_F64) return fail(MB_ERR_UNSUPPORTED, "mb_fill_uniform: fp64 blocks only (convert afterwards)");
     // generator.setSeed(partition.seed) -> XORShiftRandom.setSeed -> seed = hashSeed(s)
     const unsigned long long state0 = (unsigned long long)mb_hash_seed(partition_seed);
+    int launches = 0;
     MB_CUDA(mb::fill_uniform_f64(f64_ptr(blk), rs(blk), cs(blk), blk->rows, blk->cols, row_major ? 1 : 0, state0, first, lo,
-                                 hi, ctx->stream));
-    ctx->launches++;
+                                 hi, ctx->stream, &launches));
+    ctx->launches += launches;
     return MB_OK;
 }
 

@@ -10,8 +10,11 @@
 #include "ptx.cuh"
 #include <cuda_bf16.h>
 #include <atomic>
+#include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <mutex>
+#include <vector>
 
 namespace mb {
 
@@ -758,8 +761,51 @@ cudaError_t fill_uniform_init_tables() {
     return e;
 }
 
+// The fast kernel must reproduce the general kernel (the one pinned against the JVM stream) bit for bit.  That is checked
+// ONCE per device and process, on the device itself: two CTAs of each kernel at a far, odd stream offset, unit and affine
+// range, compared on the host (about a millisecond).  A mismatch — a compiler or driver that breaks one of the kernel's
+// exactness arguments — disables the fast kernel for the process and says so on stderr; results stay those of the general
+// kernel either way.  Returns 1 (verified) or -1 (disabled).
+static int fast_fill_state(cudaStream_t st) {
+    static std::mutex mu;
+    static std::atomic<int> state[64];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) return -1;
+    int s = state[dev].load(std::memory_order_acquire);
+    if (s) return s;
+    std::lock_guard<std::mutex> lk(mu);
+    s = state[dev].load(std::memory_order_acquire);
+    if (s) return s;
+    const long long n = 2 * 256ll * FILL_PER_THREAD;
+    const unsigned long long st0 = 0x9E3779B97F4A7C15ull;
+    const long long first = (1ll << 35) + 12345;
+    double* d = nullptr;
+    bool ok = cudaMalloc(&d, 2 * n * sizeof(double)) == cudaSuccess;
+    std::vector<double> h(ok ? 2 * n : 0);
+    for (int variant = 0; variant < 2 && ok; ++variant) {
+        const double lo = variant ? -2.0 : 0.0, hi = variant ? 5.0 : 1.0;
+        fill_uniform_kernel<<<2, 256, 0, st>>>(d, 1, n, (int)n, 1, 0, st0, first, lo, hi, 0);
+        if (variant)
+            fill_uniform_fast_kernel<false><<<2, 256, 0, st>>>(d + n, st0, first, lo, hi, 1u << 21, 1u << 4);
+        else
+            fill_uniform_fast_kernel<true><<<2, 256, 0, st>>>(d + n, st0, first, lo, hi, 1u << 21, 1u << 4);
+        ok = cudaGetLastError() == cudaSuccess &&
+             cudaMemcpyAsync(h.data(), d, 2 * n * sizeof(double), cudaMemcpyDeviceToHost, st) == cudaSuccess &&
+             cudaStreamSynchronize(st) == cudaSuccess && memcmp(h.data(), h.data() + n, n * sizeof(double)) == 0;
+    }
+    if (d) cudaFree(d);
+    if (!ok)
+        fprintf(stderr, "marlin_b200: the fast generator kernel does not reproduce the reference-exact kernel on device %d; "
+                        "it is disabled for this process (mb_fill_uniform keeps using the general kernel)\n", dev);
+    s = ok ? 1 : -1;
+    state[dev].store(s, std::memory_order_release);
+    return s;
+}
+
 cudaError_t fill_uniform_f64(double* out, long long rs, long long cs, int rows, int cols, int row_major,
-                             unsigned long long state0, long long first, double lo, double hi, cudaStream_t st) {
+                             unsigned long long state0, long long first, double lo, double hi, cudaStream_t st, int* launches) {
+    if (launches) *launches = 0;
     if (rows <= 0 || cols <= 0) return cudaSuccess;
     cudaError_t e = fill_uniform_init_tables();
     if (e != cudaSuccess) return e;
@@ -771,7 +817,8 @@ cudaError_t fill_uniform_f64(double* out, long long rs, long long cs, int rows, 
     const bool linear = row_major ? (cs == 1 && rs == cols) : (rs == 1 && cs == rows);
     int full = 0;
     static const bool no_fast = getenv("MARLIN_B200_FILL_GENERAL") != nullptr;     // test hook: force the general kernel
-    if (linear && !no_fast && ((reinterpret_cast<uintptr_t>(out) & 15) == 0)) full = (int)(total / per_block);
+    if (linear && !no_fast && ((reinterpret_cast<uintptr_t>(out) & 15) == 0) && total >= per_block && fast_fill_state(st) > 0)
+        full = (int)(total / per_block);
     if (full > 0) {
         if (lo == 0.0 && hi == 1.0)
             fill_uniform_fast_kernel<true><<<full, 256, 0, st>>>(out, state0, first, lo, hi, 1u << 21, 1u << 4);
@@ -779,9 +826,12 @@ cudaError_t fill_uniform_f64(double* out, long long rs, long long cs, int rows, 
             fill_uniform_fast_kernel<false><<<full, 256, 0, st>>>(out, state0, first, lo, hi, 1u << 21, 1u << 4);
         cudaError_t e2 = cudaGetLastError();
         if (e2 != cudaSuccess) return e2;
+        if (launches) ++*launches;
     }
-    if (blocks > full)
+    if (blocks > full) {
         fill_uniform_kernel<<<blocks - full, 256, 0, st>>>(out, rs, cs, rows, cols, row_major, state0, first, lo, hi, full);
+        if (launches) ++*launches;
+    }
     return cudaGetLastError();
 }
 

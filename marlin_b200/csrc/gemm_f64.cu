@@ -508,9 +508,13 @@ gemm_f64_dmma_grouped_kernel(const __grid_constant__ G2Params g) {
         if (en.done_ctr != nullptr) {
             // every consumer thread's stores of this tile, then ONE thread counts the tile and, if it was the entry's last,
             // publishes the completion flags with system scope (peer GPUs and the copy streams poll them).
-            // EVERY thread fences its own stores first: they may be posted writes to a peer GPU still in flight on NVLink,
-            // and the fence of the one counting thread was measured not to hold them back (a flag overtook data at 8 GPUs:
-            // profiles/r02_bench_n8_parity_failure.json).
+            // EVERY thread fences its own stores first (the conservative order: fence, CTA barrier, count).  NOTE: with the
+            // tile stored to a PEER GPU this sequence was still measured faulty — one 16x32 patch of a tile stale in about a
+            // third of the 8192^2 calls, with or without the per-thread fences (profiles/r02_fused_variants_2gpu.md,
+            // profiles/r02_bench_n8_parity_failure.json) — so csrc/dist.cu only arms done_ctr for entries whose output is in
+            // LOCAL memory; peer outputs are announced by a stream memory operation after the launch (two-launch
+            // reduce-scatter) or pushed by the copy engine (host path).  The single-launch form stays behind
+            // MARLIN_B200_FUSED_SPLIT=0 for the investigation.
             if (g.fence_all) __threadfence_system();
             asm volatile("bar.sync 1, %0;" ::"n"(NUM_CONSUMER_WARPS * 32) : "memory");
             if (cw == 0 && lane == 0) {

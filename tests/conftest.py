@@ -23,7 +23,18 @@ def _has_gpu() -> bool:
         return False
 
 
+_MULTI_PROCESS_LAST = ("test_gpu_dist_cabi.py", "test_gpu_multi.py")
+
+
 def pytest_collection_modifyitems(config, items):
+    # the multi-process GPU suites (subprocess ranks, minutes each; on a one-GPU box the ranks time-slice one device) run
+    # after everything else, so the single-process kernel parity tests are never queued behind them
+    # ... and before them, after every other single-process test, the check of WHICH generator kernel ran
+    def rank(it):
+        if Path(str(it.fspath)).name in _MULTI_PROCESS_LAST:
+            return 2
+        return 1 if it.name.startswith("test_fill_uniform_fast_kernel_is_the_one_that_ran") else 0
+    items.sort(key=rank)
     # gpu tests fail loudly on a box without a GPU only if explicitly selected; otherwise they are deselected by -m "not gpu"
     if _has_gpu():
         return

@@ -341,6 +341,27 @@ def test_fill_uniform_many_ctas_and_far_offsets(gpu, oracle, row_major):
     assert np.all(full == -1.0)                             # nothing written outside the view
 
 
+def test_fill_uniform_fast_kernel_is_the_one_that_ran(gpu, oracle):
+    """The bit-exactness assertions above hold for whichever generator kernel ran; this one shows WHICH: full CTAs of a
+    packed block go to the fast kernel (IMAD.WIDE shifts + magic-number conversion) and only the ragged tail to the general
+    one, i.e. two launches — unless the library's once-per-device self-check (fast kernel vs general kernel, on the device)
+    has disabled the fast kernel, which would be a finding in its own right.  Runs after the other single-process tests
+    (tests/conftest.py) so that such a finding cannot hide their results under -x."""
+    lib, ctx = gpu
+    rows, cols = 701, 613                                   # 6 full CTAs + a partial one
+    h = alloc(gpu, rows, cols)
+    l0 = lib.mb_launch_count(ctx)
+    nat.check(lib.mb_fill_uniform(ctx, h, 5, 0, 0.0, 1.0, 0))
+    assert lib.mb_launch_count(ctx) - l0 == 2, "fast generator kernel not active (disabled by its self-check, or MARLIN_B200_FILL_GENERAL set)"
+    assert np.array_equal(download(gpu, h, rows, cols), oracle.uniform_stream(5, 0, rows * cols).reshape((rows, cols), order="F"))
+    exact = alloc(gpu, 512, 256)                            # exactly two full CTAs: no tail launch
+    l0 = lib.mb_launch_count(ctx)
+    nat.check(lib.mb_fill_uniform(ctx, exact, 6, 9, -1.0, 1.0, 0))
+    assert lib.mb_launch_count(ctx) - l0 == 1
+    assert np.array_equal(download(gpu, exact, 512, 256),
+                          oracle.uniform_stream(6, 9, 512 * 256, -1.0, 1.0).reshape((512, 256), order="F"))
+
+
 def test_matmul_blocked_seq_order(gpu, oracle):
     """mb_matmul_blocked == BlockMatrix.multiply (BlockMatrix.scala:149-186) for a ragged (3,2,2) grid."""
     lib, ctx = gpu

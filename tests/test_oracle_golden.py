@@ -297,3 +297,40 @@ def test_dense_vec_matrix_save_formats(oracle, tmp_path):
     big = mb.DenseVecMatrix([(0, np.array([1e-7, 123456789.125, -0.5, 1e21]))])
     big.saveToFileSystem(str(tmp_path / "sci"))
     assert (tmp_path / "sci" / "part-00000").read_text() == "0:DenseVector(1.0E-7, 1.23456789125E8, -0.5, 1.0E21)\n"
+
+
+def test_fast_generator_arithmetic_equals_oracle_stream(oracle):
+    """The fast fill kernel (csrc/elementwise.cu: xs_step32 / xs_next_double) keeps the XORShift state as two 32-bit
+    halves, shifts by multiplying with 2^21 / 2^4, and converts next(26), next(27) with the 2^52 magic number and one FMA.
+    The same integer/float steps restated here must reproduce the oracle's UniformGenerator stream bit for bit — the GPU
+    test (tests/test_gpu_cabi.py) then only has to show that the kernel executes these steps."""
+    import struct
+    M32 = 0xFFFFFFFF
+
+    def step32(lo, hi):
+        for c, rsh in ((1 << 21, True), (1 << 4, False)):
+            w = lo * c
+            h = ((hi * c) & M32) + (w >> 32)
+            assert h <= M32                                   # disjoint bit ranges: the add never carries
+            hi ^= h
+            lo ^= w & M32
+            if rsh:
+                lo ^= hi >> 3
+        return lo, hi
+
+    def magic(v):                                             # __hiloint2double(0x43300000, v) - 2^52
+        return struct.unpack("<d", struct.pack("<II", v, 0x43300000))[0] - 4503599627370496.0
+
+    for seed in (123456789, 1, -77, 2 ** 40 + 5):
+        s = oracle.hash_seed(seed) & ((1 << 64) - 1)
+        lo, hi = s & M32, s >> 32
+        want = oracle.uniform_stream(seed, 0, 257)
+        for i in range(257):
+            lo, hi = step32(lo, hi)
+            da = magic(lo & 0x3FFFFFF)
+            lo, hi = step32(lo, hi)
+            db = magic(lo & 0x7FFFFFF)
+            x = da * 2.0 ** -26 + db * 2.0 ** -53              # exact: at most 53 significant bits
+            assert x == want[i], (seed, i)
+        # the 64-bit update and the halves agree
+        assert oracle._xs_step(s) == (lambda t: t[0] | (t[1] << 32))(step32(s & M32, s >> 32))
