@@ -425,7 +425,13 @@ class BlockMatrix(DistributedMatrix):
         """multiplyBy(B: BDM[Double]) :309-335 — a small local matrix times this block matrix (B replicated on every
         rank).  One block row: B * blk per block.  Several block rows: B(::, cols of block-row r) * blk, summed over r
         (reduceByKey on the unchanged BlockID, i.e. onto the block of row 0 ... as written, the keys keep their row, so
-        only blocks with equal ids are summed — with distinct ids nothing is summed; reproduced as is)."""
+        only blocks with equal ids are summed — with distinct ids nothing is summed; reproduced as is).
+
+        Two deliberate notes on labels: (1) for one block row the reference LABELS the result numRows() x B.cols (:319)
+        although the blocks it holds are B.rows x numCols(); this port labels it with the dimensions of the data, B.rows x
+        numCols() (what the several-block-rows branch at :333 also reports), so the result can be used by the next
+        operation.  (2) The column range of B at :324-330 is bounded by numCols(), not by B.cols; when that range runs past
+        B.cols Breeze's slice throws, and so does this port (no clamping)."""
         Bd = B if isinstance(B, SubMatrix) else SubMatrix(B)
         if Bd.cols != self.numRows():
             raise nat.MarlinArgumentError(nat.MB_ERR_DIM_MISMATCH, "Dimension mismatch during matrix-matrix multiplication: "
@@ -439,7 +445,9 @@ class BlockMatrix(DistributedMatrix):
         for b, blk in self.blocks:
             start = b.row * row_blk
             end = self.numCols() if (b.row + 1) * row_blk > self.numCols() else (b.row + 1) * row_blk      # :324 bounds by numCols()
-            end = min(end, Bd.cols)
+            if end > Bd.cols:                             # Breeze: B(::, start until end) out of bounds -> exception
+                raise nat.MarlinArgumentError(nat.MB_ERR_INVALID_ARG, f"multiplyBy: column range {start} until {end} of the local "
+                                              f"matrix is out of bounds ({Bd.cols} columns)")
             res.append((b, Bd.slice(0, Bd.rows, start, end).multiply(blk)))                               # :330-331
         return BlockMatrix(res, Bd.rows, self.numCols(), self.numBlksByRow(), self.numBlksByCol(), self._placement)
 
