@@ -561,9 +561,10 @@ def run_ours(args):
 
     # ---- e2e: HOST buffers in, HOST buffers out, every step ----
     # N = 1: the C-ABI entry a JVM-held BlockMatrix would bind (mb_matmul_blocked_host): pinned host tiles -> pipelined
-    #        H2D / 8 DMMA products / D2H.   N > 1: every rank uploads the blocks it owns, BlockMatrix.multiply
-    #        (NCCL tile exchange), downloads the C blocks it owns.
+    #        H2D / 8 DMMA products / D2H.   N > 1: mb_matmul_blocked_dist_host — host tiles spread over the ranks'
+    #        PCIe links, NVLink pulls, products, checkerboard reduce, D2H into shared pinned C tiles.
     e2e = None
+    e2e_cleanup = None
     if not args.no_e2e and tall:
         # every rank: its row shard as pinned row-major host rows -> mb_matmul_rowsharded_host (row chunks pipelined over
         # H2D / DMMA / D2H streams) -> pinned row-major result rows.  PCIe-bound by construction: 128 flop per byte moved.
@@ -665,6 +666,12 @@ def run_ours(args):
                 def e2e_step():
                     nat.check(lib.mb_matmul_blocked_dist_host(mesh.comm, pa, a_home, pb, b_home, g, gk, g, lens, lens, lens, pc))
 
+                def e2e_cleanup():
+                    """Unmap the shared C tiles and remove their /dev/shm names (every holder unlinks; the second unlink is a no-op)."""
+                    for t, ptr in shared.items():
+                        lib.mb_host_free_shared(f"{box[0]}_c{t}".encode(), ptr, bs_ * bs_ * 8, 1)
+                    shared.clear()
+
                 def e2e_check():
                     """The e2e result against the device-resident result of the same multiply (owner ranks, whole tiles)."""
                     Cdev = {(b.row, b.column): s_ for b, s_ in A.multiply(B).blocks}
@@ -703,6 +710,9 @@ def run_ours(args):
         if ws > 1 and not tall:
             e2e["max_abs_diff_vs_device_result"] = e2e_check()
             e2e["fraction_of_device_value"] = e2e["value"] / value
+    if e2e_cleanup is not None:
+        barrier()                      # nobody is still copying into a tile another rank is about to unmap
+        e2e_cleanup()
 
     # ---- extra (not the headline): the same multiply with the block GEMMs on the int8 tensor cores ----
     int8_split = None
