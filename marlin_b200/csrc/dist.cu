@@ -7,14 +7,18 @@
 //   * tile replication = copy-engine PULLS over NVLink peer memory (CUDA IPC), band by band, on a side stream; the
 //     persistent grouped DMMA kernel (gemm_f64.cu) starts at once and its TMA producer waits per band, so the tensor
 //     cores run on whatever has landed;
-//   * the reduceByKey of a C tile held as two partials (k split over two GPUs) is a REDUCE-SCATTER fused into the same
-//     kernel: each holder first computes the column half the OTHER one reduces, its epilogue storing straight into
+//   * the reduceByKey of a C tile held as two partials (k split over two GPUs) is a REDUCE-SCATTER done by the GEMM
+//     epilogues: each holder first computes the column half the OTHER one reduces, its epilogue storing straight into
 //     the peer's staging buffer over NVLink, then its own half as acc + staged partial; the partner's reduced half is
-//     stored, again by the epilogue, directly into the owner's C tile.  No add pass, no extra copy;
+//     stored, again by the epilogue, directly into the owner's C tile.  No add pass, no extra copy.  The two halves are
+//     two launches of the same persistent kernel with the exchange flags between them (see fused_variant below for why
+//     not one);
 //   * anything else (three or more holders, bf16 / transposed tiles) takes the staged path: partials are stored into
 //     a per-source slot of the owner's staging buffer and the owner adds them in rank order (deterministic).
-// Processes are ordered by monotonic epoch flags in exported device memory (st.release.sys / ld.acquire.sys), every
-// wait is bounded (MARLIN_B200_TIMEOUT_S, default 120 s) and reports MB_ERR_TIMEOUT instead of hanging the GPU.
+// Processes are ordered by monotonic epoch flags in exported device memory, written and awaited by stream memory
+// operations (cuStreamWriteValue64 / cuStreamWaitValue64) or polled inside the GEMM (ld.acquire).  In-kernel waits are
+// bounded (MARLIN_B200_TIMEOUT_S, default 120 s); stream-side waits cannot time out on the device, so every host-side
+// synchronisation is bounded instead and, on expiry, releases the queued waits (abort_local) and reports MB_ERR_TIMEOUT.
 #include "internal.h"
 #include "elementwise.h"
 #include "gemm_f64.h"
