@@ -133,6 +133,21 @@ NATIVE(void, fillUniform)(JNIEnv* e, jobject o, jlong ctx, jlong blk, jlong part
                           jboolean rowMajor) {
     raise(e, mb_fill_uniform(CTX(ctx), BLK(blk), partitionSeed, first, lo, hi, rowMajor ? 1 : 0));
 }
+/* ---- f4: the Breeze/LAPACK leaves of luDecompose / choleskyDecompose / inverse (matrix/DenseVecMatrix.scala:283-764) ---- */
+NATIVE(void, lu)(JNIEnv* e, jobject o, jlong ctx, jlong a, jintArray permOut) {
+    /* in place, dgetrf packing; permOut (rows entries) = the reference's permutation array: row i of L*U is row perm[i] of A */
+    const jsize n = (*e)->GetArrayLength(e, permOut);
+    int32_t* perm = (int32_t*)malloc(sizeof(int32_t) * (size_t)(n > 0 ? n : 1));
+    const int32_t rc = mb_block_lu(CTX(ctx), BLK(a), perm);
+    if (rc == MB_OK) (*e)->SetIntArrayRegion(e, permOut, 0, n, (const jint*)perm);
+    free(perm);
+    raise(e, rc);
+}
+NATIVE(void, cholesky)(JNIEnv* e, jobject o, jlong ctx, jlong a) { raise(e, mb_block_cholesky(CTX(ctx), BLK(a))); }
+NATIVE(void, inverse)(JNIEnv* e, jobject o, jlong ctx, jlong a, jlong out) { raise(e, mb_block_inverse(CTX(ctx), BLK(a), BLK(out))); }
+NATIVE(void, trsm)(JNIEnv* e, jobject o, jlong ctx, jlong t, jboolean lower, jboolean unitDiagonal, jlong b) {
+    raise(e, mb_block_trsm(CTX(ctx), BLK(t), lower ? 1 : 0, unitDiagonal ? 1 : 0, BLK(b)));
+}
 NATIVE(void, setFp64Mode)(JNIEnv* e, jobject o, jlong ctx, jint mode, jint slices) { raise(e, mb_set_fp64_mode(CTX(ctx), mode, slices)); }
 
 /* ---- a3-a6: whole multiplies on one GPU ---- */

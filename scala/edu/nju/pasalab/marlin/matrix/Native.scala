@@ -46,6 +46,12 @@ object Native {
                           rowMajor: Boolean): Unit
   @native def setFp64Mode(ctx: Long, mode: Int, slices: Int): Unit
 
+  // the Breeze/LAPACK leaves of luDecompose / choleskyDecompose / inverse (brzLU, brzCholesky, brzInv, `\`)
+  @native def lu(ctx: Long, a: Long, permOut: Array[Int]): Unit
+  @native def cholesky(ctx: Long, a: Long): Unit
+  @native def inverse(ctx: Long, a: Long, out: Long): Unit
+  @native def trsm(ctx: Long, t: Long, lower: Boolean, unitDiagonal: Boolean, b: Long): Unit
+
   // whole multiplies on one GPU
   @native def matmulBlocked(ctx: Long, aTiles: Array[Long], bTiles: Array[Long], m: Int, k: Int, n: Int,
                             cTiles: Array[Long]): Unit

@@ -85,6 +85,11 @@ class SubMatrix private[marlin] (private[marlin] val handle: Long, val rows: Int
 
   private[marlin] def sum(): Double = Native.sum(Ctx.get, handle)
 
+  /** Breeze `.copy`: a packed device copy (the in-place factorizations work on one). */
+  private[marlin] def copy(): SubMatrix = {
+    val out = fresh(rows, cols); Native.copy(Ctx.get, handle, out); new SubMatrix(out, rows, cols)
+  }
+
   private[marlin] def release(): Unit = Native.free(Ctx.get, handle)
 
   override protected def finalize(): Unit = release()

@@ -65,3 +65,19 @@ def test_scala_submatrix_keeps_the_reference_method_surface():
                 "def multiply(other: SubMatrix): SubMatrix", "def multiply(other: BDM[Double]): SubMatrix", "def multiply(b: Double): SubMatrix"):
         assert sig in text, sig
     assert "val rows: Int" in text and "val cols: Int" in text
+
+
+def test_scala_sources_only_use_declared_natives():
+    """Every `Native.x` used by the Scala host sources (SubMatrix, BlockMatrixMultiply, DenseVecMatrixNative, NativeSplit,
+    NativeRandom) is an `@native def` (or a constant) of Native.scala — the closest thing to a link check without scalac."""
+    natives = set(_scala_natives())
+    text = NATIVE.read_text()
+    consts = set(re.findall(r"\bval\s+(\w+)\s*=", text[text.index("object Native"):text.index("object Ctx")]))
+    used = {}
+    for f in (ROOT / "scala").rglob("*.scala"):
+        for name in re.findall(r"\bNative\.(\w+)", f.read_text()):
+            used.setdefault(name, f.name)
+    missing = {n: f for n, f in used.items() if n not in natives | consts}
+    assert not missing, missing
+    for name in ("matmulRowshardedHost", "lu", "cholesky", "inverse", "trsm", "fillUniform", "partitionSeeds", "matmulBlockedDist"):
+        assert name in used, name
