@@ -256,8 +256,9 @@ int32_t mb_memcpy_async(mb_ctx* ctx, void* dst, const void* src, int64_t bytes);
  * POSIX shared-memory segment used for rendezvous and per-call tile directories — no network, no torch, no MPI).
  * mb_matmul_blocked_dist is the whole of matrix/BlockMatrix.scala:159-178 — MatrixMultPartitioner mapping
  * (seq = i*n*k + j*k + kk dealt to ranks in contiguous ranges: mb_dist_plan), tile replication (NVLink peer-memory
- * pulls overlapped with the products), the m*k*n DMMA block products (one persistent launch per rank) and the
- * reduceByKey of the k partials (fused GEMM + reduce-scatter between two holders, staged adds otherwise).
+ * pulls overlapped with the products), the m*k*n DMMA block products (one persistent launch per rank; two where a k
+ * partial crosses GPUs) and the reduceByKey of the k partials (reduce-scatter by the GEMM epilogues between two holders,
+ * staged adds otherwise).
  * Every rank calls it with the same m, k, n, lengths and owner maps; A_tiles[i*k+kk] / B_tiles[kk*n+j] are non-NULL
  * exactly where the owner map names this rank; C_tiles[i*n+j] must be a preallocated (row_len[i] x col_len[j]) block
  * (F64, or F32 for BF16 inputs) wherever mb_dist_plan's c_owner names this rank, and receives the finished tile there.

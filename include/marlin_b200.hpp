@@ -46,6 +46,26 @@ private:
     mb_ctx* ctx_ = nullptr;
 };
 
+// The executors of one SparkContext on an NVSwitch box: one process per GPU, `world` of them, created collectively with
+// the same session string (include/marlin_b200.h section (e)).  A distributed BlockMatrix is, in every
+// process, the blocks that process owns plus the GLOBAL dimensions and grid; block (row, col) lives on
+// Comm::owner(row, col, blksByCol) = MatrixElemOpPartitioner partition (rdd/MatrixElemOpPartitioner.scala:16) mod world.
+class Comm {
+public:
+    Comm(int rank, int world, const std::string& session) { check(mb_comm_init(Context::get(), rank, world, session.c_str(), &c_)); }
+    ~Comm() { if (c_) mb_comm_destroy(c_); }
+    Comm(const Comm&) = delete;
+    Comm& operator=(const Comm&) = delete;
+    int rank() const { return mb_comm_rank(c_); }
+    int world() const { return mb_comm_world(c_); }
+    void barrier() { check(mb_comm_barrier(c_)); }
+    void checkPeers() { check(mb_comm_check(c_)); }          // throws if a device-side wait for a peer ever timed out
+    int owner(int row, int col, int blksByCol) const { return mb_elem_partition(row, col, blksByCol) % world(); }
+    mb_comm* handle() const { return c_; }
+private:
+    mb_comm* c_ = nullptr;
+};
+
 inline int ceilLen(long total, int parts) { return (int)std::ceil((double)total / (double)parts); }
 
 // A Breeze DenseMatrix[Double] stand-in on the host: column-major.
@@ -287,6 +307,49 @@ public:
         }
         throw std::invalid_argument("currently not supported for the two dimension of matrices");
     }
+    // multiply(other: BlockMatrix) :149-186 across the ranks of `comm`: this process passes the blocks it owns (both
+    // matrices constructed with their GLOBAL nRows / nCols / grid), and gets back the C blocks mb_dist_plan assigns to it.
+    // Replication (:161-171), the block products (:175) and the reduceByKey (:177) all happen inside ONE collective call.
+    BlockMatrix multiply(BlockMatrix& other, Comm& comm) {
+        if (nRows_ <= 0 || nCols_ <= 0 || blksByRow_ <= 0 || blksByCol_ <= 0 || other.nRows_ <= 0 || other.nCols_ <= 0 ||
+            other.blksByRow_ <= 0 || other.blksByCol_ <= 0)
+            throw std::invalid_argument("a distributed BlockMatrix needs its global dimensions and grid");
+        requireMul(nCols_, other.nRows_);
+        if (blksByCol_ != other.blksByRow_) throw std::invalid_argument("currently not supported for the two dimension of matrices");
+        const int m = blksByRow_, k = blksByCol_, n = other.blksByCol_, rank = comm.rank();
+        auto lens = [](long total, int parts) {                                    // ceil sizing, the last block takes the rest (:73-74)
+            std::vector<int32_t> v(parts);
+            const int len = ceilLen(total, parts);
+            for (int p = 0; p < parts; ++p) v[p] = (int32_t)std::max<long>(0, std::min<long>(len, total - (long)p * len));
+            return v;
+        };
+        const std::vector<int32_t> rowLen = lens(nRows_, m), kLen = lens(nCols_, k), colLen = lens(other.nCols_, n);
+        std::vector<mb_block*> A((size_t)m * k, nullptr), B((size_t)k * n, nullptr), C((size_t)m * n, nullptr);
+        std::vector<int32_t> aOwner((size_t)m * k), bOwner((size_t)k * n), prodRank((size_t)m * k * n), cOwner((size_t)m * n);
+        for (int i = 0; i < m; ++i) for (int kk = 0; kk < k; ++kk) aOwner[(size_t)i * k + kk] = ownerOf(i, kk, comm);
+        for (int kk = 0; kk < k; ++kk) for (int j = 0; j < n; ++j) bOwner[(size_t)kk * n + j] = other.ownerOf(kk, j, comm);
+        for (auto& kv : blocks) A[(size_t)kv.first.row * k + kv.first.column] = kv.second.handle();
+        for (auto& kv : other.blocks) B[(size_t)kv.first.row * n + kv.first.column] = kv.second.handle();
+        check(mb_dist_plan(m, k, n, comm.world(), prodRank.data(), cOwner.data()));
+        Blocks res;
+        for (int i = 0; i < m; ++i)
+            for (int j = 0; j < n; ++j)
+                if (cOwner[(size_t)i * n + j] == rank) {
+                    SubMatrix c = SubMatrix::empty(rowLen[i], colLen[j]);
+                    C[(size_t)i * n + j] = c.handle();
+                    res.emplace_back(BlockID(i, j), c);
+                }
+        check(mb_matmul_blocked_dist(comm.handle(), A.data(), aOwner.data(), B.data(), bOwner.data(), m, k, n, rowLen.data(), kLen.data(),
+                                     colLen.data(), MB_F64, C.data()));
+        BlockMatrix out(res, nRows_, other.nCols_, m, n);
+        out.placement_ = cOwner;                 // C(i,j) stays where its kk = 0 partial was computed (no extra move)
+        return out;
+    }
+    // Home rank of block (row, col) of a distributed matrix: MatrixElemOpPartitioner order mod world for matrices built by
+    // the caller, the plan's placement for results of a distributed multiply (so products can be chained).
+    int ownerOf(int row, int col, const Comm& comm) const {
+        return placement_.empty() ? comm.owner(row, col, blksByCol_) : placement_[(size_t)row * blksByCol_ + col];
+    }
     // multiply(other, splitMode) :131-147
     BlockMatrix multiply(BlockMatrix& other, std::tuple<int, int, int> splitMode) {
         requireMul(numCols(), other.numRows());
@@ -432,6 +495,7 @@ private:
     }
     long nRows_, nCols_;
     int blksByRow_, blksByCol_;
+    std::vector<int32_t> placement_;             // distributed results only: owner of block (i, j) at [i * blksByCol + j]
 };
 
 // ---------------------------------------------------------------------------------------------- DenseVecMatrix

@@ -37,3 +37,16 @@ def test_cpp_suite_on_gpu():
     out = subprocess.run([str(exe)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
     assert out.returncode == 0, out.stdout[-3000:]
     assert "0 failed checks" in out.stdout
+
+
+def test_cpp_rank_program_builds_and_fails_loudly_without_gpu():
+    """tests/cpp/dist_multiply.cpp (the compiled caller of the multi-GPU multiply) builds with -Werror against the host mirror
+    and, like everything else, refuses to run without a GPU."""
+    import torch
+    from tests.test_gpu_dist_cabi import build_cpp_rank_program
+    exe = build_cpp_rank_program()
+    if torch.cuda.is_available():
+        pytest.skip("GPU present: covered by test_compiled_host_mirror_multiplies_across_two_ranks")
+    out = subprocess.run([str(exe), "0", "1", "nogpu", "1"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=120)
+    assert out.returncode == 3
+    assert "no CPU fallback" in out.stdout

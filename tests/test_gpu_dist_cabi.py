@@ -73,3 +73,44 @@ def test_fused_reduce_scatter_full_size_back_to_back():
         pytest.skip("needs 2 GPUs")
     outs = _run(2, 2, False, big_fused=8192)
     assert "big fused" in "".join(o for _, o in outs)
+
+
+CPP_BIN = ROOT / "scripts" / "bin" / "dist_multiply"
+
+
+def build_cpp_rank_program() -> Path:
+    import shutil
+    from marlin_b200 import _native as nat
+    nat.load()
+    CPP_BIN.parent.mkdir(parents=True, exist_ok=True)
+    subprocess.run([shutil.which("g++") or "g++", "-std=c++17", "-O2", "-Wall", "-Wextra", "-Werror", f"-I{ROOT / 'include'}",
+                    str(ROOT / "tests" / "cpp" / "dist_multiply.cpp"), f"-L{ROOT / 'marlin_b200' / 'lib'}", "-lmarlin_b200",
+                    "-Wl,-rpath,$ORIGIN/../../marlin_b200/lib", "-o", str(CPP_BIN)], check=True, stdout=subprocess.PIPE,
+                   stderr=subprocess.STDOUT, text=True)
+    return CPP_BIN
+
+
+@pytest.mark.parametrize("dims", [(700, 528, 900, 2, 3, 2), (512, 1024, 512, 1, 2, 1), (701, 530, 899, 2, 3, 2)],
+                         ids=["even-blocks-grouped-launch", "k-split-reduce-scatter", "ragged-odd-general-path"])
+def test_compiled_host_mirror_multiplies_across_two_ranks(dims):
+    """The C++ host mirror's BlockMatrix.multiply(other, comm) (include/marlin_b200.hpp -> mb_matmul_blocked_dist) from a
+    compiled rank program, two processes (sharing the GPU on a one-GPU box): integer-valued inputs, so the C blocks are
+    compared with the host product EXACTLY.  Runs last of all (tests/conftest.py)."""
+    import torch
+    exe = build_cpp_rank_program()
+    ndev = min(2, torch.cuda.device_count())
+    session = uuid.uuid4().hex[:16]
+    env = dict(os.environ, MARLIN_B200_TIMEOUT_S="90", CUDA_DEVICE_MAX_CONNECTIONS="32")
+    procs = [subprocess.Popen([str(exe), str(r), "2", session, str(ndev)] + [str(d) for d in dims], stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True, env=env) for r in range(2)]
+    outs = []
+    for p in procs:
+        try:
+            out, _ = p.communicate(timeout=600)
+        except subprocess.TimeoutExpired:
+            for q in procs:
+                q.kill()
+            raise
+        outs.append((p.returncode, out))
+    for r, (rc, out) in enumerate(outs):
+        assert rc == 0 and f"cpp rank {r}/2 ok" in out, f"rank {r}:\n{out[-3000:]}"
